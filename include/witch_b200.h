@@ -1,0 +1,136 @@
+/*
+ * witch_b200.h -- C ABI of the B200-native eHMM score + align path for WITCH.
+ *
+ * The reference (c5shen/WITCH v1.0.10) has no FFI for this path: it shells out to HMMER 3.1b2 and talks through
+ * text files. Each entry point below replaces one of those process/file boundaries; a maintainer binds them
+ * with ctypes. Conventions: every function returns 0 on success and a negative code on
+ * error (message via witch_last_error()); the caller owns every host buffer; the library owns device memory
+ * behind opaque handles; a handle is bound to the CUDA device that was current when it was created; calls on
+ * one handle must be serialised by the caller; no callbacks. There is NO CPU fallback: without a usable CUDA
+ * device every compute entry point fails with WITCH_ERR_CUDA.
+ */
+#ifndef WITCH_B200_H
+#define WITCH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WITCH_OK 0
+#define WITCH_ERR_ARG (-1)    /* bad argument */
+#define WITCH_ERR_IO (-2)     /* cannot read / parse an HMM file */
+#define WITCH_ERR_CUDA (-3)   /* CUDA runtime error, or no device */
+#define WITCH_ERR_LIMIT (-4)  /* model or query exceeds a built-in limit */
+
+#define WITCH_ALPH_DNA 0
+#define WITCH_ALPH_RNA 1
+#define WITCH_ALPH_AMINO 2
+
+/* flag bits of witch_score's per-pair flags */
+#define WITCH_FLAG_MULTIDOMAIN 1 /* a region failed HMMER's single-domain test (rt3); kept as one envelope */
+#define WITCH_FLAG_SUMSCORE 2    /* the reconstruction ("sum") score overrode the per-sequence score */
+
+typedef struct witch_ehmm witch_ehmm;       /* an ensemble of profile HMMs resident on one GPU */
+typedef struct witch_queries witch_queries; /* a digitised, packed query set resident on one GPU */
+
+/* Thread-local description of the last error returned on this thread. */
+const char *witch_last_error(void);
+
+/* Version string "witch_b200 <semver> sm_100a". */
+const char *witch_version(void);
+
+/* Number of CUDA devices visible (0 when none / no driver). Never fails. */
+int witch_device_count(void);
+
+/*
+ * Parse n_hmm HMMER3/f ASCII profiles (what `hmmbuild` wrote, reference witch_msa/gcmm/algorithm.py:463-470),
+ * configure them in local mode (what hmmsearch / hmmalign do internally after reading the same files,
+ * algorithm.py:526-532, aligner.py:98-100) and upload them to the current device.
+ * All profiles must share one alphabet. NSEQ (reference gcmm/loader.py:40-58, HMMSubset.num_taxa) is kept.
+ */
+int witch_ehmm_create(int n_hmm, const char *const *hmm_paths, witch_ehmm **out);
+void witch_ehmm_destroy(witch_ehmm *e);
+int witch_ehmm_count(const witch_ehmm *e);
+int witch_ehmm_alphabet(const witch_ehmm *e);
+/* M[h] = model length (LENG), nseq[h] = NSEQ; either pointer may be NULL. */
+int witch_ehmm_info(const witch_ehmm *e, int32_t *M, int32_t *nseq);
+
+/*
+ * Digitise and upload n query sequences. residues = all sequences concatenated (ASCII, either case, IUPAC
+ * degenerate codes accepted), offsets[n+1] = start of each sequence in residues. Replaces the fragment-chunk
+ * FASTA files of gcmm/algorithm.py:338-385 and the per-query c1.fasta of gcmm/aligner.py:356-362.
+ */
+int witch_queries_create(const witch_ehmm *e, int n, const char *residues, const int64_t *offsets,
+                         witch_queries **out);
+void witch_queries_destroy(witch_queries *q);
+int witch_queries_count(const witch_queries *q);
+
+/*
+ * Score stage: every query against every HMM == all (HMM, chunk) `hmmsearch --cpu 1 --noali -E 99999999 --max`
+ * jobs of SearchAlgorithm.search (gcmm/algorithm.py:273-336) plus the table parse (algorithm.py:579-605).
+ * Outputs are row-major [n_queries][n_hmm] HOST arrays (any may be NULL except scores/reported):
+ *   scores    per-sequence bit score, NOT rounded (hmmsearch prints it with one decimal; see witch_weights_topk)
+ *   reported  1 if hmmsearch would list the pair (a domain envelope exists), else 0 (score is then NaN)
+ *   pre       Forward bit score before the null2 correction (hmmsearch's score + bias)
+ *   flags     WITCH_FLAG_* bits
+ */
+int witch_score(witch_ehmm *e, witch_queries *q, float *scores, uint8_t *reported, float *pre, uint8_t *flags);
+
+/*
+ * Same, results left on the device: d_scores/d_reported/(d_pre, d_flags may be NULL) are DEVICE pointers to
+ * [n_queries][n_hmm] arrays (e.g. torch tensors' data_ptr()). Work is enqueued on `stream` (a cudaStream_t
+ * passed as void*; NULL = default stream) and the call returns without synchronising.
+ */
+int witch_score_dev(witch_ehmm *e, witch_queries *q, float *d_scores, uint8_t *d_reported, float *d_pre,
+                    uint8_t *d_flags, void *stream);
+
+/*
+ * Adjusted-bitscore weights + top-k == rankBitscores + calculateWeights (gcmm/loader.py:299-332,
+ * gcmm/weighting.py:58-74):  w_i = 1 / sum_j 2^((s_j - s_i) + log2(n_j / n_i)) over the reported HMMs j of the
+ * query, sorted by weight descending, first k kept. If round_decimals >= 0 the scores are first rounded to that
+ * many decimals (1 reproduces the %6.1f text round trip of algorithm.py:596-599); -1 uses them as they are.
+ * HOST arrays: idx[n][k] (HMM index, -1 padding), w[n][k] (float64, 0 padding), count[n] (<= k).
+ * Ties in weight are broken by ascending HMM index (the reference's order there is nondeterministic).
+ */
+int witch_weights_topk(const witch_ehmm *e, const float *scores, const uint8_t *reported, int n_queries, int k,
+                       int round_decimals, int32_t *idx, double *w, int32_t *count);
+/* Device-pointer variant (all pointers are device memory), asynchronous on `stream`. */
+int witch_weights_topk_dev(const witch_ehmm *e, const float *d_scores, const uint8_t *d_reported, int n_queries,
+                           int k, int round_decimals, int32_t *d_idx, double *d_w, int32_t *d_count, void *stream);
+
+/*
+ * Align stage: for each pair p align query qidx[p] to HMM hidx[p] == one `hmmalign -o OUT HMM c1.fasta` per
+ * pair plus the Stockholm -> column-list conversion of getBackbones (gcmm/aligner.py:96-142).
+ * cols (HOST, int32) receives, at col_offsets[p] .. col_offsets[p] + L(qidx[p]), one value per residue:
+ * the 0-based match-state index, or -1 for an inserted / flanking residue.
+ */
+int witch_align(witch_ehmm *e, witch_queries *q, int n_pairs, const int32_t *qidx, const int32_t *hidx,
+                const int64_t *col_offsets, int32_t *cols);
+/* Device-pointer variant: d_qidx, d_hidx, d_col_offsets, d_cols are device memory; asynchronous on `stream`
+ * except for one internal sizing step. */
+int witch_align_dev(witch_ehmm *e, witch_queries *q, int n_pairs, const int32_t *h_qidx, const int32_t *h_hidx,
+                    const int64_t *h_col_offsets, int32_t *d_cols, void *stream);
+
+/*
+ * Instrumentation for bench.py: number of kernels this library has launched so far in this process and the
+ * accumulated device time (ms, CUDA events on the launching stream) of the dominant DP kernels since the last
+ * witch_prof_reset(). Timing is only collected while witch_prof_enable(1).
+ */
+uint64_t witch_kernel_launches(void);
+void witch_prof_enable(int on);
+void witch_prof_reset(void);
+/* which: 0 = multihit Forward/Backward parser kernel, 1 = envelope (unihit) kernels, 2 = align kernels.
+ * Returns accumulated ms and (via *cells) the DP cells those launches covered. */
+double witch_prof_get(int which, double *cells, uint64_t *launches);
+
+/* Debug / test hooks (stable, used by tests/): plain Forward and Backward scores in nats for n_pairs pairs.
+ * mode: 1 = multihit local (hmmsearch parser), 0 = unihit local (hmmalign / envelope). HOST arrays. */
+int witch_debug_fwdbwd(witch_ehmm *e, witch_queries *q, int n_pairs, const int32_t *qidx, const int32_t *hidx,
+                       int mode, float *fwd_nats, float *bwd_nats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WITCH_B200_H */

@@ -1,0 +1,131 @@
+"""Thin Python objects over the C ABI: an eHMM resident on the GPU, a packed query set, and the three stage
+calls (score, weights/top-k, align). numpy in / numpy out; the *_dev variants take raw device pointers
+(e.g. torch tensors' data_ptr()) so scores and weights never leave HBM between stages."""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import WitchError, check
+
+ALPHABETS = {0: "dna", 1: "rna", 2: "amino"}
+
+
+def _ptr(a, ctype):
+    return a.ctypes.data_as(ctypes.POINTER(ctype))
+
+
+class EHMM:
+    """Ensemble of HMMER3 profiles on the current CUDA device (reference: the hmmbuild.model.* files of
+    witch_msa/gcmm/algorithm.py:463-470 and HMMSubset of gcmm/loader.py:17-58)."""
+
+    def __init__(self, hmm_paths):
+        lib = _lib.load()
+        self.paths = [str(p) for p in hmm_paths]
+        arr = (ctypes.c_char_p * len(self.paths))(*[p.encode() for p in self.paths])
+        h = ctypes.c_void_p()
+        check(lib.witch_ehmm_create(len(self.paths), arr, ctypes.byref(h)))
+        self._h = h
+        self.n = lib.witch_ehmm_count(h)
+        self.M = np.zeros(self.n, dtype=np.int32)
+        self.nseq = np.zeros(self.n, dtype=np.int32)
+        check(lib.witch_ehmm_info(h, _ptr(self.M, ctypes.c_int32), _ptr(self.nseq, ctypes.c_int32)))
+        self.alphabet = ALPHABETS[lib.witch_ehmm_alphabet(h)]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.load().witch_ehmm_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+
+class Queries:
+    """Query sequences digitised and packed on the device."""
+
+    def __init__(self, ehmm, seqs):
+        lib = _lib.load()
+        self.ehmm = ehmm
+        seqs = [s if isinstance(s, str) else s.decode() for s in seqs]
+        self.lengths = np.array([len(s) for s in seqs], dtype=np.int64)
+        self.offsets = np.zeros(len(seqs) + 1, dtype=np.int64)
+        np.cumsum(self.lengths, out=self.offsets[1:])
+        blob = "".join(seqs).encode()
+        h = ctypes.c_void_p()
+        check(lib.witch_queries_create(ehmm._h, len(seqs), blob, _ptr(self.offsets, ctypes.c_int64), ctypes.byref(h)))
+        self._h = h
+        self.n = len(seqs)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.load().witch_queries_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+
+def score(ehmm, queries):
+    """All queries x all HMMs. Returns (scores[n,H] float32 (NaN = unreported), reported[n,H] bool,
+    pre[n,H] float32, flags[n,H] uint8)."""
+    n, H = queries.n, ehmm.n
+    scores = np.empty((n, H), dtype=np.float32)
+    rep = np.zeros((n, H), dtype=np.uint8)
+    pre = np.empty((n, H), dtype=np.float32)
+    flags = np.zeros((n, H), dtype=np.uint8)
+    check(_lib.load().witch_score(ehmm._h, queries._h, _ptr(scores, ctypes.c_float), _ptr(rep, ctypes.c_uint8),
+                                  _ptr(pre, ctypes.c_float), _ptr(flags, ctypes.c_uint8)))
+    return scores, rep.astype(bool), pre, flags
+
+
+def score_dev(ehmm, queries, d_scores, d_reported, d_pre=0, d_flags=0, stream=0):
+    check(_lib.load().witch_score_dev(ehmm._h, queries._h, d_scores, d_reported, d_pre or None, d_flags or None,
+                                      stream or None))
+
+
+def weights_topk(ehmm, scores, reported, k=10, round_decimals=1):
+    """-> (idx[n,k] int32 (-1 pad), w[n,k] float64, count[n] int32)."""
+    scores = np.ascontiguousarray(scores, dtype=np.float32)
+    rep = np.ascontiguousarray(reported, dtype=np.uint8)
+    n = scores.shape[0]
+    idx = np.full((n, k), -1, dtype=np.int32)
+    w = np.zeros((n, k), dtype=np.float64)
+    cnt = np.zeros(n, dtype=np.int32)
+    check(_lib.load().witch_weights_topk(ehmm._h, _ptr(scores, ctypes.c_float), _ptr(rep, ctypes.c_uint8), n, k,
+                                         round_decimals, _ptr(idx, ctypes.c_int32), _ptr(w, ctypes.c_double),
+                                         _ptr(cnt, ctypes.c_int32)))
+    return idx, w, cnt
+
+
+def weights_topk_dev(ehmm, d_scores, d_reported, n, k, round_decimals, d_idx, d_w, d_count, stream=0):
+    check(_lib.load().witch_weights_topk_dev(ehmm._h, d_scores, d_reported, n, k, round_decimals, d_idx, d_w, d_count,
+                                             stream or None))
+
+
+def align(ehmm, queries, qidx, hidx):
+    """Optimal-accuracy column lists for the given (query, HMM) pairs. -> list of int32 arrays."""
+    qidx = np.ascontiguousarray(qidx, dtype=np.int32)
+    hidx = np.ascontiguousarray(hidx, dtype=np.int32)
+    lens = queries.lengths[qidx]
+    off = np.zeros(len(qidx) + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    cols = np.full(int(off[-1]) if len(qidx) else 0, -1, dtype=np.int32)
+    if len(qidx):
+        check(_lib.load().witch_align(ehmm._h, queries._h, len(qidx), _ptr(qidx, ctypes.c_int32),
+                                      _ptr(hidx, ctypes.c_int32), _ptr(off, ctypes.c_int64),
+                                      _ptr(cols, ctypes.c_int32)))
+    return [cols[off[p]:off[p + 1]] for p in range(len(qidx))]
+
+
+def debug_fwdbwd(ehmm, queries, qidx, hidx, multihit):
+    qidx = np.ascontiguousarray(qidx, dtype=np.int32)
+    hidx = np.ascontiguousarray(hidx, dtype=np.int32)
+    f = np.zeros(len(qidx), dtype=np.float32)
+    b = np.zeros(len(qidx), dtype=np.float32)
+    check(_lib.load().witch_debug_fwdbwd(ehmm._h, queries._h, len(qidx), _ptr(qidx, ctypes.c_int32),
+                                         _ptr(hidx, ctypes.c_int32), 1 if multihit else 0,
+                                         _ptr(f, ctypes.c_float), _ptr(b, ctypes.c_float)))
+    return f, b
+
+
+def kernel_launches():
+    return int(_lib.load().witch_kernel_launches())

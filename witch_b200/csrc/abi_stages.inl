@@ -1,0 +1,292 @@
+// Stage orchestration behind the C ABI (included by witch_abi.cu).
+
+static int wave_C_for(const witch_ehmm *) { return 8; }
+
+struct WaveBucket { int Lcap; std::vector<WaveItem> items; };
+
+// Launches the wavefront kernel over `items` (any order); outputs indexed by WaveItem::pair.
+template <bool ALIGN>
+static void run_wave(witch_ehmm *e, witch_queries *q, std::vector<WaveItem> items, float *d_envsc, float *d_domcorr,
+                     int *d_cols, const long long *d_coloff, float *d_dbg_fwd, float *d_dbg_bwd, cudaStream_t st) {
+    if (items.empty()) return;
+    constexpr int C = 8;
+    const int SW = 32 * C;
+    // buckets by envelope length so that scratch is not sized by the single longest item
+    const int caps[] = {256, 512, 1024, 2048, 4096, 1 << 30};
+    std::vector<WaveBucket> buckets(6);
+    for (auto &it : items) {
+        int b = 0;
+        while (it.Ls > caps[b]) b++;
+        buckets[b].items.push_back(it);
+    }
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    const double budget = std::min<double>(64.0e9, 0.5 * (double)(free_b + e->bytes.n));
+    for (auto &bk : buckets) {
+        if (bk.items.empty()) continue;
+        int Lcap = 0, max_strips = 1, maxM = 0;
+        double cells = 0;
+        for (auto &it : bk.items) {
+            Lcap = std::max(Lcap, it.Ls);
+            maxM = std::max(maxM, e->M[it.h]);
+            cells += (double)it.Ls * e->M[it.h];
+        }
+        max_strips = (maxM + SW - 1) / SW;
+        std::stable_sort(bk.items.begin(), bk.items.end(), [&](const WaveItem &a, const WaveItem &b) {
+            if (a.h != b.h) return e->M[a.h] != e->M[b.h] ? e->M[a.h] > e->M[b.h] : a.h < b.h;
+            return a.Ls > b.Ls;
+        });
+        std::vector<int> gfirst, gcount;
+        for (size_t i = 0; i < bk.items.size();) {
+            size_t j = i;
+            while (j < bk.items.size() && bk.items[j].h == bk.items[i].h && j - i < (size_t)WAVE_WARPS) j++;
+            gfirst.push_back((int)i); gcount.push_back((int)(j - i));
+            i = j;
+        }
+        const WaveLayout lay = wave_layout(Lcap, max_strips, C, ALIGN);
+        const size_t smem = (size_t)q->nsym * max_strips * SW * sizeof(float);
+        if (smem > 200 * 1024) throw std::runtime_error("emission table does not fit shared memory");
+        auto kern = wave_kernel<C, ALIGN>;
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 1;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WAVE_WARPS * 32, smem));
+        if (occ < 1) throw std::runtime_error("wave kernel cannot be resident");
+        long long grid = std::min<long long>((long long)gfirst.size(), (long long)e->num_sms * occ);
+        const long long max_slots = (long long)(budget / (double)lay.total);
+        if (max_slots < WAVE_WARPS) throw std::runtime_error("not enough device memory for the wave scratch");
+        grid = std::max<long long>(1, std::min<long long>(grid, max_slots / WAVE_WARPS));
+        e->bytes.alloc((size_t)grid * WAVE_WARPS * lay.total);
+        DevBuf<WaveItem> ditems; ditems.upload(bk.items, st);
+        DevBuf<int> dgf, dgc; dgf.upload(gfirst, st); dgc.upload(gcount, st);
+        e->counter.alloc(64);
+        CUDA_TRY(cudaMemsetAsync(e->counter.p, 0, sizeof(unsigned), st));
+        WaveWork wk;
+        wk.items = ditems.p; wk.group_first = dgf.p; wk.group_count = dgc.p; wk.ngroups = (int)gfirst.size();
+        wk.counter = e->counter.p; wk.scratch = (char *)e->bytes.p; wk.slot_bytes = lay.total; wk.Lcap = Lcap;
+        wk.max_strips = max_strips; wk.envsc = d_envsc; wk.domcorr = d_domcorr; wk.cols = d_cols; wk.col_off = d_coloff;
+        wk.dbg_fwd = d_dbg_fwd; wk.dbg_bwd = d_dbg_bwd;
+        {
+            ScopedTimer tm(ALIGN ? 2 : 1, st, cells);
+            kern<<<(int)grid, WAVE_WARPS * 32, smem, st>>>(e->view(), q->view(), wk);
+            g_launches++;
+            CUDA_TRY(cudaGetLastError());
+        }
+        CUDA_TRY(cudaStreamSynchronize(st));  // ditems/dgf/dgc are freed at scope exit
+    }
+}
+
+static void check_handles(witch_ehmm *e, witch_queries *q) {
+    if (!e || !q) throw std::invalid_argument("null handle");
+    if (e->alph != q->alph) throw std::invalid_argument("queries were digitised for another alphabet");
+    CUDA_TRY(cudaSetDevice(e->device));
+}
+
+extern "C" int witch_score_dev(witch_ehmm *e, witch_queries *q, float *d_scores, uint8_t *d_reported, float *d_pre,
+                               uint8_t *d_flags, void *stream) {
+    try {
+        check_handles(e, q);
+        if (!d_scores || !d_reported) return fail(WITCH_ERR_ARG, "witch_score: scores/reported must not be NULL");
+        cudaStream_t st = (cudaStream_t)stream;
+        const int nq = q->n, H = e->H;
+        if (nq == 0) return WITCH_OK;
+        std::vector<int> qs(nq), hs(H);
+        std::iota(qs.begin(), qs.end(), 0);
+        std::iota(hs.begin(), hs.end(), 0);
+        run_parser(e, q, qs, hs, nullptr, st);
+        // envelope list -> wave items (host side)
+        std::vector<PairParse> parse((size_t)nq * H);
+        CUDA_TRY(cudaMemcpyAsync(parse.data(), e->parse.p, parse.size() * sizeof(PairParse), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        std::vector<int> env_base((size_t)nq * H, 0);
+        std::vector<WaveItem> items;
+        for (int qi = 0; qi < nq; qi++)
+            for (int h = 0; h < H; h++) {
+                const PairParse &pp = parse[(size_t)qi * H + h];
+                env_base[(size_t)qi * H + h] = (int)items.size();
+                for (int k = 0; k < pp.nenv; k++) {
+                    WaveItem it;
+                    it.q = qi; it.h = h; it.i0 = pp.env_i[k]; it.Ls = pp.env_j[k] - pp.env_i[k] + 1;
+                    it.pair = (int)items.size();
+                    items.push_back(it);
+                }
+            }
+        e->f1.alloc(items.size() + 1);
+        e->f2.alloc(items.size() + 1);
+        e->i3.upload(env_base, st);
+        run_wave<false>(e, q, items, e->f1.p, e->f2.p, nullptr, nullptr, nullptr, nullptr, st);
+        const long long np = (long long)nq * H;
+        finalize_scores_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(e->parse.p, q->dlen.p, nq, H, e->i3.p, e->f1.p,
+                                                                           e->f2.p, d_scores, d_reported, d_pre, d_flags);
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+        return WITCH_OK;
+    } catch (const std::invalid_argument &ex) {
+        return fail(WITCH_ERR_ARG, ex.what());
+    } catch (const std::exception &ex) {
+        return fail(WITCH_ERR_CUDA, ex.what());
+    }
+}
+
+extern "C" int witch_score(witch_ehmm *e, witch_queries *q, float *scores, uint8_t *reported, float *pre, uint8_t *flags) {
+    try {
+        check_handles(e, q);
+        if (!scores || !reported) return fail(WITCH_ERR_ARG, "witch_score: scores/reported must not be NULL");
+        const size_t np = (size_t)q->n * e->H;
+        if (np == 0) return WITCH_OK;
+        DevBuf<float> ds, dp;
+        DevBuf<uint8_t> dr, df;
+        ds.alloc(np); dp.alloc(np); dr.alloc(np); df.alloc(np);
+        int rc = witch_score_dev(e, q, ds.p, dr.p, dp.p, df.p, nullptr);
+        if (rc != WITCH_OK) return rc;
+        CUDA_TRY(cudaMemcpy(scores, ds.p, np * sizeof(float), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(reported, dr.p, np, cudaMemcpyDeviceToHost));
+        if (pre) CUDA_TRY(cudaMemcpy(pre, dp.p, np * sizeof(float), cudaMemcpyDeviceToHost));
+        if (flags) CUDA_TRY(cudaMemcpy(flags, df.p, np, cudaMemcpyDeviceToHost));
+        return WITCH_OK;
+    } catch (const std::invalid_argument &ex) {
+        return fail(WITCH_ERR_ARG, ex.what());
+    } catch (const std::exception &ex) {
+        return fail(WITCH_ERR_CUDA, ex.what());
+    }
+}
+
+extern "C" int witch_weights_topk_dev(const witch_ehmm *e, const float *d_scores, const uint8_t *d_reported, int nq, int k,
+                                      int round_decimals, int32_t *d_idx, double *d_w, int32_t *d_count, void *stream) {
+    try {
+        if (!e || !d_scores || !d_reported || !d_idx || !d_w || !d_count || k <= 0 || nq < 0)
+            return fail(WITCH_ERR_ARG, "witch_weights_topk: bad arguments");
+        CUDA_TRY(cudaSetDevice(e->device));
+        if (nq == 0) return WITCH_OK;
+        const int warps = 4;
+        weights_topk_kernel<<<(nq + warps - 1) / warps, warps * 32, 0, (cudaStream_t)stream>>>(
+            d_scores, d_reported, e->dnseq.p, nq, e->H, k, round_decimals, d_idx, d_w, d_count);
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+        return WITCH_OK;
+    } catch (const std::exception &ex) {
+        return fail(WITCH_ERR_CUDA, ex.what());
+    }
+}
+
+extern "C" int witch_weights_topk(const witch_ehmm *e, const float *scores, const uint8_t *reported, int nq, int k,
+                                  int round_decimals, int32_t *idx, double *w, int32_t *count) {
+    try {
+        if (!e || !scores || !reported || !idx || !w || !count || k <= 0 || nq < 0)
+            return fail(WITCH_ERR_ARG, "witch_weights_topk: bad arguments");
+        CUDA_TRY(cudaSetDevice(e->device));
+        if (nq == 0) return WITCH_OK;
+        const size_t np = (size_t)nq * e->H;
+        DevBuf<float> ds; DevBuf<uint8_t> dr; DevBuf<int> di, dc; DevBuf<double> dw;
+        ds.alloc(np); dr.alloc(np); di.alloc((size_t)nq * k); dw.alloc((size_t)nq * k); dc.alloc(nq);
+        CUDA_TRY(cudaMemcpy(ds.p, scores, np * sizeof(float), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(dr.p, reported, np, cudaMemcpyHostToDevice));
+        int rc = witch_weights_topk_dev(e, ds.p, dr.p, nq, k, round_decimals, di.p, dw.p, dc.p, nullptr);
+        if (rc != WITCH_OK) return rc;
+        CUDA_TRY(cudaMemcpy(idx, di.p, (size_t)nq * k * sizeof(int), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(w, dw.p, (size_t)nq * k * sizeof(double), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(count, dc.p, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost));
+        return WITCH_OK;
+    } catch (const std::exception &ex) {
+        return fail(WITCH_ERR_CUDA, ex.what());
+    }
+}
+
+static std::vector<WaveItem> align_items(witch_ehmm *e, witch_queries *q, int n_pairs, const int32_t *qidx,
+                                         const int32_t *hidx) {
+    std::vector<WaveItem> items;
+    items.reserve(n_pairs);
+    for (int p = 0; p < n_pairs; p++) {
+        if (qidx[p] < 0 || qidx[p] >= q->n || hidx[p] < 0 || hidx[p] >= e->H)
+            throw std::invalid_argument("witch_align: pair index out of range");
+        if (q->len[qidx[p]] <= 0) continue;
+        WaveItem it;
+        it.q = qidx[p]; it.h = hidx[p]; it.i0 = 1; it.Ls = q->len[qidx[p]]; it.pair = p;
+        items.push_back(it);
+    }
+    return items;
+}
+
+extern "C" int witch_align_dev(witch_ehmm *e, witch_queries *q, int n_pairs, const int32_t *qidx, const int32_t *hidx,
+                               const int64_t *col_offsets, int32_t *d_cols, void *stream) {
+    try {
+        check_handles(e, q);
+        if (n_pairs < 0 || (n_pairs > 0 && (!qidx || !hidx || !col_offsets || !d_cols)))
+            return fail(WITCH_ERR_ARG, "witch_align: bad arguments");
+        if (n_pairs == 0) return WITCH_OK;
+        cudaStream_t st = (cudaStream_t)stream;
+        std::vector<WaveItem> items = align_items(e, q, n_pairs, qidx, hidx);
+        std::vector<long long> co(col_offsets, col_offsets + n_pairs);
+        DevBuf<long long> dco; dco.upload(co, st);
+        run_wave<true>(e, q, items, nullptr, nullptr, d_cols, dco.p, nullptr, nullptr, st);
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return WITCH_OK;
+    } catch (const std::invalid_argument &ex) {
+        return fail(WITCH_ERR_ARG, ex.what());
+    } catch (const std::exception &ex) {
+        return fail(WITCH_ERR_CUDA, ex.what());
+    }
+}
+
+extern "C" int witch_align(witch_ehmm *e, witch_queries *q, int n_pairs, const int32_t *qidx, const int32_t *hidx,
+                           const int64_t *col_offsets, int32_t *cols) {
+    try {
+        check_handles(e, q);
+        if (n_pairs < 0 || (n_pairs > 0 && (!qidx || !hidx || !col_offsets || !cols)))
+            return fail(WITCH_ERR_ARG, "witch_align: bad arguments");
+        if (n_pairs == 0) return WITCH_OK;
+        long long total = 0;
+        for (int p = 0; p < n_pairs; p++) {
+            if (qidx[p] < 0 || qidx[p] >= q->n) return fail(WITCH_ERR_ARG, "witch_align: pair index out of range");
+            total = std::max<long long>(total, col_offsets[p] + q->len[qidx[p]]);
+        }
+        DevBuf<int> dc; dc.alloc((size_t)total);
+        CUDA_TRY(cudaMemset(dc.p, 0xff, (size_t)total * sizeof(int)));
+        int rc = witch_align_dev(e, q, n_pairs, qidx, hidx, col_offsets, dc.p, nullptr);
+        if (rc != WITCH_OK) return rc;
+        CUDA_TRY(cudaMemcpy(cols, dc.p, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost));
+        return WITCH_OK;
+    } catch (const std::invalid_argument &ex) {
+        return fail(WITCH_ERR_ARG, ex.what());
+    } catch (const std::exception &ex) {
+        return fail(WITCH_ERR_CUDA, ex.what());
+    }
+}
+
+extern "C" int witch_debug_fwdbwd(witch_ehmm *e, witch_queries *q, int n_pairs, const int32_t *qidx, const int32_t *hidx,
+                                  int mode, float *fwd_nats, float *bwd_nats) {
+    try {
+        check_handles(e, q);
+        if (n_pairs <= 0 || !qidx || !hidx || !fwd_nats || !bwd_nats) return fail(WITCH_ERR_ARG, "bad arguments");
+        if (mode == 1) {
+            // multihit parser: run per distinct (q, h) through Family S
+            std::vector<int> qs(qidx, qidx + n_pairs), hs(hidx, hidx + n_pairs);
+            std::sort(qs.begin(), qs.end()); qs.erase(std::unique(qs.begin(), qs.end()), qs.end());
+            std::sort(hs.begin(), hs.end()); hs.erase(std::unique(hs.begin(), hs.end()), hs.end());
+            DevBuf<float> db; db.alloc((size_t)q->n * e->H);
+            run_parser(e, q, qs, hs, db.p, nullptr);
+            std::vector<PairParse> parse((size_t)q->n * e->H);
+            std::vector<float> bw((size_t)q->n * e->H);
+            CUDA_TRY(cudaMemcpy(parse.data(), e->parse.p, parse.size() * sizeof(PairParse), cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(bw.data(), db.p, bw.size() * sizeof(float), cudaMemcpyDeviceToHost));
+            for (int p = 0; p < n_pairs; p++) {
+                const size_t ix = (size_t)qidx[p] * e->H + hidx[p];
+                fwd_nats[p] = parse[ix].fwd_bits * 0.69314718056f;
+                bwd_nats[p] = bw[ix];
+            }
+        } else {
+            std::vector<WaveItem> items = align_items(e, q, n_pairs, qidx, hidx);
+            DevBuf<float> df, db, d1, d2;
+            df.alloc(n_pairs); db.alloc(n_pairs); d1.alloc(n_pairs); d2.alloc(n_pairs);
+            CUDA_TRY(cudaMemset(df.p, 0, n_pairs * sizeof(float)));
+            CUDA_TRY(cudaMemset(db.p, 0, n_pairs * sizeof(float)));
+            run_wave<false>(e, q, items, d1.p, d2.p, nullptr, nullptr, df.p, db.p, nullptr);
+            CUDA_TRY(cudaMemcpy(fwd_nats, df.p, n_pairs * sizeof(float), cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(bwd_nats, db.p, n_pairs * sizeof(float), cudaMemcpyDeviceToHost));
+        }
+        return WITCH_OK;
+    } catch (const std::invalid_argument &ex) {
+        return fail(WITCH_ERR_ARG, ex.what());
+    } catch (const std::exception &ex) {
+        return fail(WITCH_ERR_CUDA, ex.what());
+    }
+}

@@ -1,0 +1,45 @@
+// Device-side views shared by all kernels (plain structs passed by value at launch).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace witch {
+
+constexpr int MAX_SYM = 32;   // emission rows a query set may use (Kp of amino is 29)
+constexpr int MAX_ENV = 6;    // envelopes kept per (query, HMM) pair
+constexpr float LOG2E_F = 1.4426950408889634f;
+
+// Ensemble of profiles in HBM: nine per-node float arrays (probability space), one emission-odds table.
+// Layout: every HMM h owns a zero-padded slice [poff[h], poff[h] + stride[h]) of each transition array
+// (index = node k, node 0 and nodes > M are all-zero) and a [Kp][stride[h]] block of `emis` at eoff[h].
+struct DevEhmm {
+    const float *tMM, *tMI, *tMD, *tIM, *tII, *tDM, *tDD, *entry;
+    const float *emis;
+    const int *M;
+    const int *stride;
+    const long long *poff;
+    const long long *eoff;
+    int H;
+    int Kp;
+};
+
+// Query set in HBM: residues as dense symbol codes (one byte each, 0..nsym-1), concatenated.
+struct DevQueries {
+    const uint8_t *dsq;
+    const long long *off;  // [n+1]
+    const int *len;        // [n]
+    int n;
+    int nsym;              // distinct symbols present in the set
+    int symrow[MAX_SYM];   // dense code -> alphabet symbol code (row of the emission table)
+};
+
+// Result of the multihit parser pass for one pair.
+struct PairParse {
+    float fwd_bits;        // log2 of the multihit Forward probability (odds space)
+    int nenv;              // number of envelopes (regions); 0 => pair is not reported
+    int flags;             // WITCH_FLAG_MULTIDOMAIN if any region failed the single-domain test
+    int env_i[MAX_ENV];    // 1-based inclusive envelope coordinates
+    int env_j[MAX_ENV];
+};
+
+}  // namespace witch

@@ -1,0 +1,430 @@
+// Family S: multihit-local Forward + Backward "parser" pass with posterior domain decoding and region
+// detection (hmmsearch's ForwardParser / BackwardParser / DomainDecoding / region heuristics, SURVEY.md 8(a)
+// "Score semantics" items 3-6).
+//
+// Mapping: one CTA per (query, HMM) pair, row-synchronous. Thread j owns C consecutive model columns and keeps
+// their transition parameters and the M/I/D state of the current row in REGISTERS; match emission odds for the
+// symbols present in the query set are staged in shared memory (vector-load friendly layout). The multihit
+// feedback B(i) <- E(i) makes every row depend on a CTA-wide sum, so a row is two (Forward) or three (Backward)
+// barrier-separated stages; the in-row D->D chain is resolved exactly with a two-level (warp shuffle, then
+// cross-warp) scan of affine maps whose multiplicative parts are per-thread constants.
+// Arithmetic: FP32 probability space with power-of-two row rescaling (the exponent is an exact integer).
+#pragma once
+#include "device_types.cuh"
+
+namespace witch {
+
+struct ParserWork {
+    const int *hmms;    // HMM indices of this launch class
+    int nh;
+    const int *qorder;  // query indices, longest first
+    int nq;
+    int Lcap;           // scratch rows per CTA (>= max query length + 1)
+    float *scratch;     // per CTA: 6*(Lcap+1) Forward specials + 3*(Lcap+1) decode arrays + 2*(Lcap+1) prefix sums
+    unsigned *counter;  // dynamic work counter
+    PairParse *out;     // [n_queries * H]
+    float *dbg_bwd;     // optional [n_queries * H] backward total (nats), debug only
+};
+
+__device__ __forceinline__ int fexp(float v) { return ((__float_as_int(v) >> 23) & 0xff) - 127; }
+__device__ __forceinline__ float pow2i(int e) {
+    e = e < -126 ? -126 : (e > 127 ? 127 : e);
+    return __int_as_float((e + 127) << 23);
+}
+
+template <int C>
+__device__ __forceinline__ void load_cols(const float *__restrict__ p, long long k, float (&r)[C]) {
+#pragma unroll
+    for (int c = 0; c < C; c++) r[c] = __ldg(p + k + c);
+}
+
+// shared-memory emission row for symbol x: element (thread j, column cc)
+template <int C>
+__device__ __forceinline__ int emis_index(int T, int j, int cc) {
+    if (C % 4 == 0) return (cc >> 2) * (T * 4) + j * 4 + (cc & 3);
+    return j * C + cc;
+}
+
+template <int C>
+__device__ __forceinline__ void load_emis(const float *row, int T, int j, float (&e)[C]) {
+    if (C % 4 == 0) {
+#pragma unroll
+        for (int v = 0; v < C / 4; v++) {
+            float4 t = *reinterpret_cast<const float4 *>(row + v * (T * 4) + j * 4);
+            e[4 * v] = t.x; e[4 * v + 1] = t.y; e[4 * v + 2] = t.z; e[4 * v + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < C; c++) e[c] = row[j * C + c];
+    }
+}
+
+constexpr int S_RED = 32;  // max warps per CTA
+
+template <int C>
+__global__ void __launch_bounds__(C == 4 ? 512 : (C == 8 ? 384 : 320)) mh_parser_kernel(DevEhmm E, DevQueries Q, ParserWork Wk) {
+    extern __shared__ float smem[];
+    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5, NW = T >> 5;
+    const int TC = T * C;
+    float *emis_s = smem;                       // [nsym][TC]
+    float *s_tot = emis_s + (size_t)Q.nsym * TC;  // [32]
+    float *s_es = s_tot + S_RED;
+    float *s_pw = s_es + S_RED;
+    float *s_bM = s_pw + S_RED;  // [2][32]
+    float *s_bI = s_bM + 2 * S_RED;
+    float *s_bD = s_bI + 2 * S_RED;
+    __shared__ int s_item;
+
+    const int stride_scr = 11 * (Wk.Lcap + 1);
+    float *Fs = Wk.scratch + (size_t)blockIdx.x * stride_scr;  // [(L+1)][6]: N,B,E,J,C,exp
+    float *dPB = Fs + 6 * (Wk.Lcap + 1);                       // P(B at i)
+    float *dPE = dPB + (Wk.Lcap + 1);                          // P(E at i)
+    float *dMO = dPE + (Wk.Lcap + 1);                          // mocc[i]
+    float *dBT = dMO + (Wk.Lcap + 1);                          // btot prefix
+    float *dET = dBT + (Wk.Lcap + 1);                          // etot prefix
+
+    const long long nitems = (long long)Wk.nh * Wk.nq;
+    int loaded_h = -1;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = (int)atomicAdd(Wk.counter, 1u);
+        __syncthreads();
+        const long long item = s_item;
+        if (item >= nitems) break;
+        const int h = Wk.hmms[item % Wk.nh];
+        const int q = Wk.qorder[item / Wk.nh];
+        const int L = Q.len[q];
+        const long long qoff = Q.off[q];
+        const long long po = E.poff[h];
+        PairParse *res = Wk.out + (size_t)q * E.H + h;
+        if (L <= 0) {
+            if (tid == 0) { res->fwd_bits = 0.f; res->nenv = 0; res->flags = 0; }
+            continue;
+        }
+        // ---- stage the emission rows of this HMM (only when the HMM changes) ----
+        if (h != loaded_h) {
+            const int st = E.stride[h];
+            const float *eg = E.emis + E.eoff[h];
+            for (int idx = tid; idx < Q.nsym * TC; idx += T) {
+                int x = idx / TC, col = idx - x * TC;
+                int j = col / C, cc = col - j * C;
+                float v = (col < st - 1) ? __ldg(eg + (size_t)Q.symrow[x] * st + 1 + col) : 0.f;
+                emis_s[(size_t)x * TC + emis_index<C>(T, j, cc)] = v;
+            }
+            loaded_h = h;
+        }
+        const int k0 = tid * C;  // owns model columns k0+1 .. k0+C
+        const float nj = 1.0f;
+        const float pmove = (2.0f + nj) / ((float)L + 2.0f + nj), ploop = 1.0f - pmove;
+        const float EC = 0.5f, EJ = 0.5f;
+
+        // =========================== Forward ===========================
+        float pa[C], pb[C], pg[C], pmd[C], pdd[C], pmi[C], pii[C], pen[C], pDD[C];
+        load_cols<C>(E.tMM + po, k0, pa);   // into column k0+1+cc from node k0+cc
+        load_cols<C>(E.tIM + po, k0, pb);
+        load_cols<C>(E.tDM + po, k0, pg);
+        load_cols<C>(E.tMD + po, k0, pmd);
+        load_cols<C>(E.tDD + po, k0, pdd);
+        load_cols<C>(E.tMI + po, k0 + 1, pmi);
+        load_cols<C>(E.tII + po, k0 + 1, pii);
+        load_cols<C>(E.entry + po, k0 + 1, pen);
+        const float mdo = __ldg(E.tMD + po + k0 + C), ddo = __ldg(E.tDD + po + k0 + C);
+        pDD[0] = 1.f;
+#pragma unroll
+        for (int c = 1; c < C; c++) pDD[c] = pDD[c - 1] * pdd[c];
+        float coef[5], Cexcl;
+        {
+            float Pc = pDD[C - 1] * ddo;
+#pragma unroll
+            for (int s = 0; s < 5; s++) {
+                float up = __shfl_up_sync(0xffffffffu, Pc, 1 << s);
+                coef[s] = (lane >= (1 << s)) ? Pc : 0.f;
+                if (lane >= (1 << s)) Pc *= up;
+            }
+            Cexcl = __shfl_up_sync(0xffffffffu, Pc, 1);
+            if (lane == 0) Cexcl = 1.f;
+            if (lane == 31) s_pw[w] = Pc;
+        }
+        float sM[C], sI[C], sD[C];
+#pragma unroll
+        for (int c = 0; c < C; c++) { sM[c] = 0.f; sI[c] = 0.f; sD[c] = 0.f; }
+        float xN = 1.f, xB = pmove, xE = 0.f, xJ = 0.f, xC = 0.f;
+        int sF = 0;
+        if (tid == 0) { Fs[0] = xN; Fs[1] = xB; Fs[2] = 0.f; Fs[3] = 0.f; Fs[4] = 0.f; Fs[5] = 0.f; }
+        __syncthreads();  // emis_s, s_pw ready
+        int xres = Q.dsq[qoff];
+        for (int i = 1; i <= L; i++) {
+            float scl = 1.f;
+            if (i > 1) {  // post(i-1)
+                float Et = 0.f;
+                for (int ww = 0; ww < NW; ww++) Et += s_es[ww];
+                xE = Et; xJ = xJ * ploop + Et * EJ; xC = xC * ploop + Et * EC; xN *= ploop; xB = (xN + xJ) * pmove;
+                if (Et > 1.0e12f) {
+                    int e = fexp(Et);
+                    scl = pow2i(-e); sF += e;
+                    xE *= scl; xJ *= scl; xC *= scl; xN *= scl; xB *= scl;
+#pragma unroll
+                    for (int c = 0; c < C; c++) { sM[c] *= scl; sI[c] *= scl; sD[c] *= scl; }
+                }
+                if (tid == 0) {
+                    float *r = Fs + 6 * (i - 1);
+                    r[0] = xN; r[1] = xB; r[2] = xE; r[3] = xJ; r[4] = xC; r[5] = (float)sF;
+                }
+            }
+            // pre(i)
+            float e[C];
+            load_emis<C>(emis_s + (size_t)xres * TC, T, tid, e);
+            if (i < L) xres = Q.dsq[qoff + i];
+            float mL = __shfl_up_sync(0xffffffffu, sM[C - 1], 1);
+            float iL = __shfl_up_sync(0xffffffffu, sI[C - 1], 1);
+            float dL = __shfl_up_sync(0xffffffffu, sD[C - 1], 1);
+            if (lane == 0) {
+                if (w > 0 && i > 1) {
+                    const int bb = ((i - 1) & 1) * S_RED + w - 1;
+                    mL = s_bM[bb] * scl; iL = s_bI[bb] * scl; dL = s_bD[bb] * scl;
+                } else { mL = 0.f; iL = 0.f; dL = 0.f; }
+            }
+            float nM[C], nI[C];
+#pragma unroll
+            for (int c = C - 1; c >= 0; c--) {
+                float pm = c > 0 ? sM[c - 1] : mL, pi = c > 0 ? sI[c - 1] : iL, pd = c > 0 ? sD[c - 1] : dL;
+                nI[c] = sM[c] * pmi[c] + sI[c] * pii[c];
+                float acc = xB * pen[c];
+                acc = fmaf(pm, pa[c], acc); acc = fmaf(pi, pb[c], acc); acc = fmaf(pd, pg[c], acc);
+                nM[c] = acc * e[c];
+            }
+            float dl[C];
+            dl[0] = 0.f;
+#pragma unroll
+            for (int c = 1; c < C; c++) dl[c] = fmaf(nM[c - 1], pmd[c], dl[c - 1] * pdd[c]);
+            float y = fmaf(nM[C - 1], mdo, dl[C - 1] * ddo);
+#pragma unroll
+            for (int s = 0; s < 5; s++) {
+                float up = __shfl_up_sync(0xffffffffu, y, 1 << s);
+                y = fmaf(coef[s], up, y);
+            }
+            float yex = __shfl_up_sync(0xffffffffu, y, 1);
+            if (lane == 0) yex = 0.f;
+            if (lane == 31) {
+                s_tot[w] = y;
+                s_bM[(i & 1) * S_RED + w] = nM[C - 1];
+                s_bI[(i & 1) * S_RED + w] = nI[C - 1];
+            }
+            __syncthreads();
+            // mid(i)
+            float Z = 0.f;
+            for (int ww = 0; ww < w; ww++) Z = fmaf(s_pw[ww], Z, s_tot[ww]);
+            const float X = fmaf(Cexcl, Z, yex);
+            float es = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                sD[c] = fmaf(pDD[c], X, dl[c]);
+                sM[c] = nM[c]; sI[c] = nI[c];
+                es += sM[c] + sD[c];
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) es += __shfl_xor_sync(0xffffffffu, es, o);
+            if (lane == 0) s_es[w] = es;
+            if (lane == 31) s_bD[(i & 1) * S_RED + w] = sD[C - 1];
+            __syncthreads();
+        }
+        {  // post(L)
+            float Et = 0.f;
+            for (int ww = 0; ww < NW; ww++) Et += s_es[ww];
+            xE = Et; xJ = xJ * ploop + Et * EJ; xC = xC * ploop + Et * EC; xN *= ploop; xB = (xN + xJ) * pmove;
+            if (tid == 0) {
+                float *r = Fs + 6 * L;
+                r[0] = xN; r[1] = xB; r[2] = xE; r[3] = xJ; r[4] = xC; r[5] = (float)sF;
+            }
+        }
+        const float Tm = xC * pmove;  // total = Tm * 2^sF
+        const int sT = sF;
+        const float fwd_bits = log2f(Tm) + (float)sT;
+
+        // =========================== Backward ===========================
+        // parameters leaving the owned columns
+        load_cols<C>(E.tMM + po, k0 + 1, pa);
+        load_cols<C>(E.tIM + po, k0 + 1, pb);
+        load_cols<C>(E.tDM + po, k0 + 1, pg);
+        load_cols<C>(E.tMD + po, k0 + 1, pmd);
+        load_cols<C>(E.tDD + po, k0 + 1, pdd);
+        // pmi, pii, pen already hold tMI, tII, entry of the owned columns
+        pDD[C - 1] = pdd[C - 1];
+#pragma unroll
+        for (int c = C - 2; c >= 0; c--) pDD[c] = pdd[c] * pDD[c + 1];
+        __syncthreads();  // everyone done reading s_pw / s_es of the forward pass
+        {
+            float Pc = pDD[0];
+#pragma unroll
+            for (int s = 0; s < 5; s++) {
+                float dn = __shfl_down_sync(0xffffffffu, Pc, 1 << s);
+                coef[s] = (lane + (1 << s) < 32) ? Pc : 0.f;
+                if (lane + (1 << s) < 32) Pc *= dn;
+            }
+            Cexcl = __shfl_down_sync(0xffffffffu, Pc, 1);
+            if (lane == 31) Cexcl = 1.f;
+            if (lane == 0) s_pw[w] = Pc;
+        }
+#pragma unroll
+        for (int c = 0; c < C; c++) { sM[c] = 0.f; sI[c] = 0.f; sD[c] = 0.f; }
+        float bN = 0.f, bJ = 0.f, bC = 0.f, bE = 0.f;
+        int sB = 0;
+        const float invT = 1.0f / Tm;
+        for (int i = L; i >= 0; i--) {
+            // pre(i): consume row i+1 and residue i+1
+            float mn[C], mnR[C];
+            float eR = 0.f;
+            if (i < L) {
+                const int xr = Q.dsq[qoff + i];
+                float e[C];
+                const float *erow = emis_s + (size_t)xr * TC;
+                load_emis<C>(erow, T, tid, e);
+                if (tid + 1 < T) eR = erow[emis_index<C>(T, tid + 1, 0)];
+#pragma unroll
+                for (int c = 0; c < C; c++) mn[c] = sM[c] * e[c];
+            } else {
+#pragma unroll
+                for (int c = 0; c < C; c++) mn[c] = 0.f;
+            }
+            float nb = __shfl_down_sync(0xffffffffu, mn[0], 1);
+            if (lane == 31) nb = (w + 1 < NW && i < L) ? s_bM[((i + 1) & 1) * S_RED + w + 1] * eR : 0.f;
+            float bp = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                mnR[c] = (c < C - 1) ? mn[c + 1] : nb;
+                bp = fmaf(mn[c], pen[c], bp);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) bp += __shfl_xor_sync(0xffffffffu, bp, o);
+            if (lane == 0) s_es[w] = bp;
+            float Mp[C], nI[C], tm[C];
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                Mp[c] = fmaf(mnR[c], pa[c], sI[c] * pmi[c]);
+                nI[c] = fmaf(mnR[c], pb[c], sI[c] * pii[c]);
+                tm[c] = mnR[c] * pg[c];
+            }
+            // Forward specials needed by the decoding of row i (thread 0 only)
+            float f0[6], f1[6];
+            if (tid == 0) {
+#pragma unroll
+                for (int z = 0; z < 6; z++) { f1[z] = Fs[6 * i + z]; f0[z] = (i > 0) ? Fs[6 * (i - 1) + z] : 0.f; }
+            }
+            __syncthreads();
+            // mid(i)
+            float Bi = 0.f;
+            for (int ww = 0; ww < NW; ww++) Bi += s_es[ww];
+            if (i == L) { bC = pmove; bJ = 0.f; bN = 0.f; }
+            else { bJ = bJ * ploop + Bi * pmove; bC = bC * ploop; bN = bN * ploop + Bi * pmove; }
+            bE = bJ * EJ + bC * EC;
+            {
+                float big = fmaxf(fmaxf(bN, bJ), Bi);
+                if (big > 1.0e9f) {
+                    int e = fexp(big);
+                    float scl = pow2i(-e);
+                    sB += e;
+                    bN *= scl; bJ *= scl; bC *= scl; bE *= scl; Bi *= scl;
+#pragma unroll
+                    for (int c = 0; c < C; c++) { Mp[c] *= scl; nI[c] *= scl; tm[c] *= scl; }
+                }
+            }
+            if (tid == 0) {
+                // P(B at i), P(E at i), mocc[i]  
+                const float fii = exp2f(f1[5] + (float)(sB - sT)) * invT;
+                dPB[i] = f1[1] * Bi * fii;
+                dPE[i] = f1[2] * bE * fii;
+                if (i > 0) {
+                    const float fpi = exp2f(f0[5] + (float)(sB - sT)) * invT * ploop;
+                    dMO[i] = 1.0f - (f0[0] * bN + f0[3] * bJ + f0[4] * bC) * fpi;
+                } else dMO[0] = 0.f;
+            }
+            if (i == 0) break;
+            float dl[C];
+            dl[C - 1] = tm[C - 1] + bE;
+#pragma unroll
+            for (int c = C - 2; c >= 0; c--) dl[c] = fmaf(dl[c + 1], pdd[c], tm[c] + bE);
+            float y = dl[0];
+#pragma unroll
+            for (int s = 0; s < 5; s++) {
+                float dn = __shfl_down_sync(0xffffffffu, y, 1 << s);
+                y = fmaf(coef[s], dn, y);
+            }
+            float yex = __shfl_down_sync(0xffffffffu, y, 1);
+            if (lane == 31) yex = 0.f;
+            if (lane == 0) s_tot[w] = y;
+            __syncthreads();
+            // post(i)
+            float Z = 0.f;
+            for (int ww = NW - 1; ww > w; ww--) Z = fmaf(s_pw[ww], Z, s_tot[ww]);
+            const float X = fmaf(Cexcl, Z, yex);  // D(i, first column of the right neighbour)
+#pragma unroll
+            for (int c = C - 1; c >= 0; c--) {
+                sD[c] = fmaf(pDD[c], X, dl[c]);
+                const float dr = (c < C - 1) ? sD[c + 1] : X;
+                sM[c] = fmaf(pmd[c], dr, Mp[c] + bE);
+                sI[c] = nI[c];
+            }
+            if (lane == 0) s_bM[(i & 1) * S_RED + w] = sM[0];
+            __syncthreads();
+        }
+        if (Wk.dbg_bwd != nullptr && tid == 0)
+            Wk.dbg_bwd[(size_t)q * E.H + h] = (logf(bN) + (float)sB * 0.69314718056f);
+
+        // =========================== regions (warp 0) ===========================
+        __syncthreads();
+        if (w == 0) {
+            const float rt1 = 0.25f, rt2 = 0.10f, rt3 = 0.20f;
+            // prefix sums btot[i] = sum_{i'<i} P(B at i'), etot[i] = sum_{i'<=i} P(E at i')
+            float cb = 0.f, ce = 0.f;
+            for (int base = 0; base <= L; base += 32) {
+                int idx = base + lane;
+                float vb = (idx >= 1 && idx <= L) ? dPB[idx - 1] : 0.f;
+                float ve = (idx >= 1 && idx <= L) ? dPE[idx] : 0.f;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    float ub = __shfl_up_sync(0xffffffffu, vb, o), ue = __shfl_up_sync(0xffffffffu, ve, o);
+                    if (lane >= o) { vb += ub; ve += ue; }
+                }
+                vb += cb; ve += ce;
+                if (idx <= L) { dBT[idx] = vb; dET[idx] = ve; }
+                cb = __shfl_sync(0xffffffffu, vb, 31); ce = __shfl_sync(0xffffffffu, ve, 31);
+            }
+            __syncwarp();
+            int nenv = 0, flags = 0, i0 = -1, trig = 0;
+            for (int base = 1; base <= L; base += 32) {
+                const int idx = base + lane;
+                float mo = 0.f, db = 0.f, de = 0.f;
+                if (idx <= L) { mo = dMO[idx]; db = dPB[idx - 1]; de = dPE[idx]; }
+                const int lim = min(32, L - base + 1);
+                for (int z = 0; z < lim; z++) {
+                    const float m = __shfl_sync(0xffffffffu, mo, z), b = __shfl_sync(0xffffffffu, db, z),
+                                ee = __shfl_sync(0xffffffffu, de, z);
+                    const int j = base + z;
+                    if (!trig) {
+                        if (m - b < rt2) i0 = j; else if (i0 == -1) i0 = j;
+                        if (m >= rt1) trig = 1;
+                    } else if (m - ee < rt2) {
+                        // region i0..j : single- or multi-domain?
+                        float mx = -1.f;
+                        const float eb = dET[i0 - 1], bj = dBT[j];
+                        for (int zz = i0 + lane; zz <= j; zz += 32)
+                            mx = fmaxf(mx, fminf(dET[zz] - eb, bj - dBT[zz - 1]));
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                        if (mx >= rt3) flags |= 1;
+                        if (nenv < MAX_ENV && lane == 0) { res->env_i[nenv] = i0; res->env_j[nenv] = j; }
+                        nenv++;
+                        i0 = -1; trig = 0;
+                    }
+                }
+            }
+            if (lane == 0) {
+                res->fwd_bits = fwd_bits;
+                res->nenv = nenv < MAX_ENV ? nenv : MAX_ENV;
+                res->flags = flags | (nenv > MAX_ENV ? 4 : 0);
+            }
+        }
+    }
+}
+
+}  // namespace witch

@@ -1,0 +1,107 @@
+// Small per-pair / per-query kernels: per-sequence score assembly (SURVEY.md 8(a) "Score semantics" item 8) and
+// adjusted-bitscore weights + top-k (reference witch_msa/gcmm/weighting.py:58-74, gcmm/loader.py:318-330).
+#pragma once
+#include "device_types.cuh"
+
+namespace witch {
+
+// One thread per (query, HMM) pair.
+__global__ void finalize_scores_kernel(const PairParse *parse, const int *qlen, int nq, int H,
+                                       const int *env_base,      // [nq*H] first envelope slot of the pair
+                                       const float *envsc, const float *domcorr,  // per envelope slot (nats)
+                                       float *scores, uint8_t *reported, float *pre, uint8_t *flags) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= (long long)nq * H) return;
+    const int q = (int)(p / H);
+    const PairParse pp = parse[p];
+    const float LN2 = 0.69314718056f;
+    const float L = (float)qlen[q];
+    int fl = pp.flags & 1;
+    float score = __int_as_float(0x7fc00000), prev = score;
+    uint8_t rep = 0;
+    if (qlen[q] > 0) {
+        const float p1 = L / (L + 1.0f);
+        const float nullsc = L * logf(p1) + logf(1.0f - p1);
+        const float fwd = pp.fwd_bits * LN2;
+        prev = (fwd - nullsc) / LN2;
+        if (pp.nenv > 0) {
+            const float omega = 1.0f / 256.0f;
+            float sb = 0.f, S = 0.f, corr = 0.f;
+            int Ld = 0;
+            const int b = env_base[p];
+            for (int e = 0; e < pp.nenv; e++) {
+                const float dc = domcorr[b + e], es = envsc[b + e];
+                sb += dc;
+                if (es - dc > 0.f) { S += es; Ld += pp.env_j[e] - pp.env_i[e] + 1; corr += dc; }
+            }
+            const float seqbias = log1pf(omega * expf(sb));
+            float seq = (fwd - (nullsc + seqbias)) / LN2;
+            const float b2 = log1pf(omega * expf(corr));
+            float sum = S + (L - (float)Ld) * logf(L / (L + 3.0f));
+            sum = (sum - (nullsc + b2)) / LN2;
+            if (Ld > 0 && sum > seq) { seq = sum; fl |= 2; }
+            score = seq;
+            rep = 1;
+        }
+    }
+    scores[p] = score;
+    reported[p] = rep;
+    if (pre) pre[p] = prev;
+    if (flags) flags[p] = (uint8_t)fl;
+}
+
+// One warp per query: base-2 softmax over the reported HMMs with log2(NSEQ) offsets, top-k by weight.
+__global__ void weights_topk_kernel(const float *scores, const uint8_t *reported, const int *nseq, int nq, int H, int k,
+                                    int round_decimals, int *idx, double *wout, int *count) {
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const float *s = scores + (size_t)q * H;
+    const uint8_t *r = reported + (size_t)q * H;
+    const unsigned FULL = 0xffffffffu;
+    double scale = 1.0;
+    for (int d = 0; d < round_decimals; d++) scale *= 10.0;
+    auto a_of = [&](int h) -> double {
+        double v = (double)s[h];
+        if (round_decimals >= 0) v = rint(v * scale) / scale;  // the "%6.1f" text round trip
+        return v + log2((double)nseq[h]);
+    };
+    double m = -1.0e300;
+    int n = 0;
+    for (int h = lane; h < H; h += 32)
+        if (r[h]) { m = fmax(m, a_of(h)); n++; }
+    for (int o = 16; o > 0; o >>= 1) { m = fmax(m, __shfl_xor_sync(FULL, m, o)); n += __shfl_xor_sync(FULL, n, o); }
+    double sum = 0.0;
+    for (int h = lane; h < H; h += 32)
+        if (r[h]) sum += exp2(a_of(h) - m);
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+    const int keep = n < k ? n : k;
+    // k rounds of arg-max over a = s + log2 n (same order as the weights); ties -> smaller HMM index
+    double last_a = 1.0e300;
+    int last_h = -1;
+    for (int j = 0; j < k; j++) {
+        double ba = -1.0e300;
+        int bh = 0x7fffffff;
+        if (j < keep) {
+            for (int h = lane; h < H; h += 32) {
+                if (!r[h]) continue;
+                const double a = a_of(h);
+                const bool after = (a < last_a) || (a == last_a && h > last_h);  // not yet emitted
+                if (after && (a > ba || (a == ba && h < bh))) { ba = a; bh = h; }
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                const double oa = __shfl_xor_sync(FULL, ba, o);
+                const int oh = __shfl_xor_sync(FULL, bh, o);
+                if (oa > ba || (oa == ba && oh < bh)) { ba = oa; bh = oh; }
+            }
+            last_a = ba; last_h = bh;
+        }
+        if (lane == 0) {
+            idx[(size_t)q * k + j] = (j < keep) ? bh : -1;
+            wout[(size_t)q * k + j] = (j < keep) ? exp2(ba - m) / sum : 0.0;
+        }
+    }
+    if (lane == 0) count[q] = keep;
+}
+
+}  // namespace witch

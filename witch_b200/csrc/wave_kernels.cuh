@@ -1,0 +1,635 @@
+// Family W: unihit-local Forward / Backward / posterior decoding / optimal accuracy as a warp-per-pair,
+// strip-mined WAVEFRONT (SURVEY.md 8(a) "Score semantics" item 7 and "Align semantics").
+//
+// In unihit mode B(i) = N(i)*move is known in closed form, so no row needs a model-wide sum before the next row
+// can start. One warp owns one (query, HMM, envelope) item and sweeps the model in strips of 32*C columns:
+// lane l keeps the transition parameters of its C columns and the previous row's M/I/D in registers and, at step
+// t, works on row i = t - l. Every dependency (diagonal, vertical, and the in-row D->D chain) then comes from
+// the lane's own registers or from the left neighbour's values of the previous step: 4 shuffles per step, no
+// barrier, no scan, and the D chain is exact. Strip boundaries (last column of every row) go through a small
+// per-item array in L2. Forward rows are kept in a "wave layout" [strip][t][lane][C] so that the Backward sweep,
+// which visits tile row t = L+31-t', reads them back fully coalesced for posterior decoding.
+// Scaling: one power-of-two exponent per warp and step (exact integer bookkeeping), renormalised every 8 steps.
+#pragma once
+#include "device_types.cuh"
+#include "parser_kernel.cuh"
+
+namespace witch {
+
+struct WaveItem {
+    int q, h;      // query, HMM
+    int i0, Ls;    // envelope start (1-based) and length; align: i0 = 1, Ls = L
+    int pair;      // output slot (envelope list index or align pair index)
+};
+
+struct WaveWork {
+    const WaveItem *items;
+    const int *group_first;  // groups of consecutive items sharing one HMM (one CTA processes a group)
+    const int *group_count;
+    int ngroups;
+    unsigned *counter;
+    // per-warp-slot scratch
+    char *scratch;
+    long long slot_bytes;
+    int Lcap;       // max Ls in this launch
+    int max_strips;
+    // outputs (envelope mode)
+    float *envsc;   // [nitems] ln P(envelope | unihit model)
+    float *domcorr; // [nitems] sum of ln null2 over the envelope
+    // outputs (align mode)
+    int *cols;               // concatenated column lists
+    const long long *col_off;  // [npairs]
+    float *dbg_fwd, *dbg_bwd;  // optional per item totals (nats)
+};
+
+constexpr int WAVE_WARPS = 4;  // warps per CTA (they share one HMM's emission table in shared memory)
+constexpr int W_SCALE_EVERY = 8;
+
+// scratch layout helper (all offsets in bytes, per warp slot)
+struct WaveLayout {
+    long long tileM, tileI, gF, bnd, rows, bits, total;
+    int TT;
+};
+__host__ __device__ inline WaveLayout wave_layout(int Lcap, int max_strips, int C, bool align) {
+    WaveLayout w;
+    w.TT = Lcap + 32;
+    long long tile = (long long)max_strips * w.TT * 32 * C * 4;
+    long long o = 0;
+    w.tileM = o; o += tile;
+    w.tileI = o; o += tile;
+    w.gF = o; o += (long long)max_strips * w.TT * 4;
+    w.bnd = o; o += (long long)6 * (Lcap + 2) * 4;    // bndM,bndI,bndD,bndE,bndG,(spare)
+    w.rows = o; o += (long long)10 * (Lcap + 2) * 4;  // FC,FCg,NB,NBg,NOA,PPC,EOA,KE,...
+    w.bits = o; if (align) o += (long long)max_strips * w.TT * 32 * 4;
+    w.total = (o + 255) / 256 * 256;
+    return w;
+}
+
+// comparator for select_e (HMMER visits cells in striped order; M uses >=, D uses >): returns true if
+// candidate (v2,isD2,ord2) replaces current (v1,isD1,ord1)
+__device__ __forceinline__ bool oa_e_better(float v2, int d2, int o2, float v1, int d1, int o1) {
+    if (v2 > v1) return true;
+    if (v2 < v1) return false;
+    if (d1 != d2) return d2 == 0;           // M beats D on ties
+    return d2 == 0 ? (o2 > o1) : (o2 < o1);  // last M in visiting order, first D in visiting order
+}
+
+template <int C, bool ALIGN>
+__global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQueries Q, WaveWork Wk) {
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __shared__ int s_group;
+    __shared__ float s_n2[WAVE_WARPS][MAX_SYM];
+    float *emis_s = smem;  // [nsym][Mstr] in strip-interleaved layout
+    const WaveLayout lay = wave_layout(Wk.Lcap, Wk.max_strips, C, ALIGN);
+    char *slot = Wk.scratch + ((long long)blockIdx.x * WAVE_WARPS + w) * Wk.slot_bytes;
+    float *tileM = (float *)(slot + lay.tileM), *tileI = (float *)(slot + lay.tileI);
+    int *gFarr = (int *)(slot + lay.gF);
+    const int LB = Wk.Lcap + 2;
+    float *bndM = (float *)(slot + lay.bnd), *bndI = bndM + LB, *bndD = bndI + LB, *bndE = bndD + LB;
+    int *bndG = (int *)(bndE + LB);
+    float *rFC = (float *)(slot + lay.rows);
+    int *rFCg = (int *)(rFC + LB);
+    float *rNB = (float *)(rFCg + LB);
+    int *rNBg = (int *)(rNB + LB);
+    float *rNOA = (float *)(rNBg + LB), *rPPC = rNOA + LB, *rEOA = rPPC + LB;
+    int *rKE = (int *)(rEOA + LB);
+    unsigned *bits = (unsigned *)(slot + lay.bits);
+    const int TT = lay.TT;
+    const int SW = 32 * C;  // strip width
+
+    int loaded_h = -1, Mstr = 0;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_group = (int)atomicAdd(Wk.counter, 1u);
+        __syncthreads();
+        const int grp = s_group;
+        if (grp >= Wk.ngroups) break;
+        const int gfirst = Wk.group_first[grp], gcount = Wk.group_count[grp];
+        const int h = Wk.items[gfirst].h;
+        const int Mh = E.M[h];
+        const int nstrips = (Mh + SW - 1) / SW;
+        if (h != loaded_h) {
+            Mstr = nstrips * SW;
+            const int st = E.stride[h];
+            const float *eg = E.emis + E.eoff[h];
+            for (int idx = threadIdx.x; idx < Q.nsym * Mstr; idx += blockDim.x) {
+                int x = idx / Mstr, col = idx - x * Mstr;
+                int s = col / SW, r = col - s * SW, l = r / C, cc = r - l * C;
+                float v = (col < st - 1) ? __ldg(eg + (size_t)Q.symrow[x] * st + 1 + col) : 0.f;
+                emis_s[(size_t)x * Mstr + s * SW + emis_index<C>(32, l, cc)] = v;
+            }
+            loaded_h = h;
+        }
+        __syncthreads();
+        if (w >= gcount) continue;
+        const WaveItem it = Wk.items[gfirst + w];
+        const int Ls = it.Ls, Lfull = Q.len[it.q];
+        const uint8_t *dsq = Q.dsq + Q.off[it.q] + (it.i0 - 1);  // dsq[i-1] = residue i of the envelope
+        const long long po = E.poff[h];
+        const float pmove = 2.0f / ((float)Lfull + 2.0f), ploop = 1.0f - pmove;
+        const unsigned FULL = 0xffffffffu;
+        const int nsteps = Ls + 31;
+
+        // ======================================= Forward =======================================
+        float xCv = 0.f;  // C special (lane 31 of the last strip), at exponent xCg
+        int xCg = 0;
+        float Tm = 1.f; int gT = 0;
+        for (int s = 0; s < nstrips; s++) {
+            const long long k0 = (long long)s * SW + lane * C;  // owns columns k0+1..k0+C
+            float pa[C], pb[C], pg[C], pmd[C], pdd[C], pmi[C], pii[C], pen[C];
+            load_cols<C>(E.tMM + po, k0, pa); load_cols<C>(E.tIM + po, k0, pb); load_cols<C>(E.tDM + po, k0, pg);
+            load_cols<C>(E.tMD + po, k0, pmd); load_cols<C>(E.tDD + po, k0, pdd);
+            load_cols<C>(E.tMI + po, k0 + 1, pmi); load_cols<C>(E.tII + po, k0 + 1, pii);
+            load_cols<C>(E.entry + po, k0 + 1, pen);
+            float sM[C], sI[C], sD[C];
+#pragma unroll
+            for (int c = 0; c < C; c++) { sM[c] = 0.f; sI[c] = 0.f; sD[c] = 0.f; }
+            float rM = 0.f, rI = 0.f, rD = 0.f;      // row i-1 at the column left of the owned block
+            float ep = 0.f;                          // running E(i) partial of the lane's last row
+            int g = (s > 0) ? bndG[1] : 0;           // warp exponent
+            float xBs = pmove * pow2i(-g);           // pmove * N(i-1) * 2^-g for the lane's next row
+            const bool last = (s == nstrips - 1);
+            const float *emis_strip = emis_s + s * SW;
+            float *tM = tileM + (size_t)s * TT * SW, *tI = tileI + (size_t)s * TT * SW;
+            if (last) { xCv = 0.f; xCg = g; }
+            for (int t = 1; t <= nsteps; t++) {
+                const int i = t - lane;
+                const bool act = (i >= 1 && i <= Ls);
+                // values of row i at the column left of my block: left lane's last step, or the strip boundary
+                float cM = __shfl_up_sync(FULL, sM[C - 1], 1);
+                float cI = __shfl_up_sync(FULL, sI[C - 1], 1);
+                float cD = __shfl_up_sync(FULL, sD[C - 1], 1);
+                float cE = __shfl_up_sync(FULL, ep, 1);
+                if (lane == 0) {
+                    if (s > 0 && act) {
+                        const float f = pow2i(bndG[i] - g);
+                        cM = bndM[i] * f; cI = bndI[i] * f; cD = bndD[i] * f; cE = bndE[i] * f;
+                    } else { cM = 0.f; cI = 0.f; cD = 0.f; cE = 0.f; }
+                }
+                if (act) {
+                    float e[C];
+                    load_emis<C>(emis_strip + (size_t)dsq[i - 1] * Mstr, 32, lane, e);
+                    float nM[C], nI[C], nD[C];
+#pragma unroll
+                    for (int c = C - 1; c >= 0; c--) {
+                        float pm = c > 0 ? sM[c - 1] : rM, pi = c > 0 ? sI[c - 1] : rI, pd = c > 0 ? sD[c - 1] : rD;
+                        nI[c] = sM[c] * pmi[c] + sI[c] * pii[c];
+                        float acc = xBs * pen[c];
+                        acc = fmaf(pm, pa[c], acc); acc = fmaf(pi, pb[c], acc); acc = fmaf(pd, pg[c], acc);
+                        nM[c] = acc * e[c];
+                    }
+                    nD[0] = fmaf(cM, pmd[0], cD * pdd[0]);
+#pragma unroll
+                    for (int c = 1; c < C; c++) nD[c] = fmaf(nM[c - 1], pmd[c], nD[c - 1] * pdd[c]);
+                    float es = cE;
+#pragma unroll
+                    for (int c = 0; c < C; c++) { sM[c] = nM[c]; sI[c] = nI[c]; sD[c] = nD[c]; es += nM[c] + nD[c]; }
+                    ep = es;
+                    rM = cM; rI = cI; rD = cD;
+                    xBs *= ploop;
+                    // keep the row for posterior decoding (wave layout)
+                    float *dm = tM + ((size_t)t * 32 + lane) * C, *di = tI + ((size_t)t * 32 + lane) * C;
+                    if (C % 4 == 0) {
+#pragma unroll
+                        for (int v = 0; v < C / 4; v++) {
+                            reinterpret_cast<float4 *>(dm)[v] = make_float4(nM[4 * v], nM[4 * v + 1], nM[4 * v + 2], nM[4 * v + 3]);
+                            reinterpret_cast<float4 *>(di)[v] = make_float4(nI[4 * v], nI[4 * v + 1], nI[4 * v + 2], nI[4 * v + 3]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < C; c++) { dm[c] = nM[c]; di[c] = nI[c]; }
+                    }
+                    if (lane == 31) {
+                        if (!last) { bndM[i] = sM[C - 1]; bndI[i] = sI[C - 1]; bndD[i] = sD[C - 1]; bndE[i] = ep; bndG[i] = g; }
+                        else {
+                            // C(i) = C(i-1)*loop + E(i)   (unihit: E->C = 1), with exponent alignment
+                            const float f = pow2i(xCg - g);
+                            xCv = xCv * f * ploop + ep; xCg = g;
+                            rFC[i] = xCv; rFCg[i] = g;
+                        }
+                    }
+                }
+                if (lane == 0) gFarr[s * TT + t] = g;
+                if ((t & (W_SCALE_EVERY - 1)) == 0) {
+                    float mx = 0.f;
+#pragma unroll
+                    for (int c = 0; c < C; c++) mx = fmaxf(mx, fmaxf(sM[c], fmaxf(sI[c], sD[c])));
+                    mx = fmaxf(mx, ep);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
+                    int e_need = (mx > 1048576.f) ? fexp(mx) : 0;
+                    if (s > 0) {
+                        int ahead = bndG[min(Ls, t + W_SCALE_EVERY)] - 40 - g;
+                        e_need = max(e_need, ahead);
+                    }
+                    if (e_need > 0) {
+                        const float f = pow2i(-e_need);
+                        g += e_need;
+#pragma unroll
+                        for (int c = 0; c < C; c++) { sM[c] *= f; sI[c] *= f; sD[c] *= f; }
+                        rM *= f; rI *= f; rD *= f; ep *= f; xBs *= f;
+                    }
+                }
+            }
+            if (last) {
+                xCv = __shfl_sync(FULL, xCv, 31); xCg = __shfl_sync(FULL, xCg, 31);
+            }
+            __syncwarp();
+        }
+        Tm = xCv * pmove; gT = xCg;  // P = Tm * 2^gT
+        const float fwd_nats = logf(Tm) + (float)gT * 0.69314718056f;
+        if (lane == 0 && Wk.dbg_fwd) Wk.dbg_fwd[it.pair] = fwd_nats;
+        const float invT = 1.0f / Tm;
+
+        // ======================================= Backward =======================================
+        // lane l processes row i = Ls - (t' - (31 - l)), rows Ls .. 0 (row 0 only feeds the B special)
+        float xNv = 0.f; int xNg = 0;  // N special (lane 0 of strip 0)
+        float accI = 0.f;             // expected insert uses (envelope mode)
+        if (!ALIGN && lane < MAX_SYM) s_n2[w][lane] = 0.f;
+        __syncwarp();
+        const int nstepsB = Ls + 1 + 31;
+        for (int s = nstrips - 1; s >= 0; s--) {
+            const long long k0 = (long long)s * SW + lane * C;
+            float oMM[C], oIM[C], oDM[C], oMD[C], oDD[C], oMI[C], oII[C], pen[C];
+            load_cols<C>(E.tMM + po, k0 + 1, oMM); load_cols<C>(E.tIM + po, k0 + 1, oIM);
+            load_cols<C>(E.tDM + po, k0 + 1, oDM); load_cols<C>(E.tMD + po, k0 + 1, oMD);
+            load_cols<C>(E.tDD + po, k0 + 1, oDD); load_cols<C>(E.tMI + po, k0 + 1, oMI);
+            load_cols<C>(E.tII + po, k0 + 1, oII); load_cols<C>(E.entry + po, k0 + 1, pen);
+            float sM[C], sI[C], sD[C], accM[C];
+#pragma unroll
+            for (int c = 0; c < C; c++) { sM[c] = 0.f; sI[c] = 0.f; sD[c] = 0.f; accM[c] = 0.f; }
+            float rMb = 0.f;   // Mb(i+1, first column right of my block)
+            float bp = 0.f;    // running B(i) partial
+            const bool lastS = (s == nstrips - 1), firstS = (s == 0);
+            int g = lastS ? 0 : bndG[Ls];
+            float ebs = pmove * pow2i(-g);  // E(i) = C_b(i) = pmove * loop^(Ls-i), scaled
+            const float *emis_strip = emis_s + s * SW;
+            // emission of the first column of the right neighbour's block (k0 + C + 1)
+            const int rs = (lane == 31) ? s + 1 : s, rl = (lane == 31) ? 0 : lane + 1;
+            const bool hasR = !(lastS && lane == 31);
+            const float *emis_right = emis_s + rs * SW + emis_index<C>(32, rl, 0);
+            float *tM = tileM + (size_t)s * TT * SW, *tI = tileI + (size_t)s * TT * SW;
+            if (firstS) { xNv = 0.f; xNg = g; }
+            for (int tp = 0; tp < nstepsB; tp++) {
+                const int i = Ls - (tp - (31 - lane));
+                const bool act = (i >= 0 && i <= Ls);
+                float cMb = __shfl_down_sync(FULL, sM[0], 1);   // Mb(i, right column)   (row i of the right lane)
+                float cDb = __shfl_down_sync(FULL, sD[0], 1);   // Db(i, right column)
+                float cB = __shfl_down_sync(FULL, bp, 1);
+                if (lane == 31) {
+                    if (!lastS && act) {
+                        const float f = pow2i(bndG[i] - g);
+                        cMb = bndM[i] * f; cDb = bndD[i] * f; cB = bndE[i] * f;
+                    } else { cMb = 0.f; cDb = 0.f; cB = 0.f; }
+                }
+                const int tF = Ls + 31 - tp;  // forward tile row holding row i of this lane (valid for i >= 1)
+                if (act) {
+                    float mn[C], mnR;
+                    if (i < Ls) {
+                        const int xr = dsq[i];
+                        float e[C];
+                        load_emis<C>(emis_strip + (size_t)xr * Mstr, 32, lane, e);
+#pragma unroll
+                        for (int c = 0; c < C; c++) mn[c] = sM[c] * e[c];
+                        mnR = hasR ? rMb * emis_right[(size_t)xr * Mstr] : 0.f;
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < C; c++) mn[c] = 0.f;
+                        mnR = 0.f;
+                    }
+                    float bs = cB;
+#pragma unroll
+                    for (int c = 0; c < C; c++) bs = fmaf(mn[c], pen[c], bs);
+                    bp = bs;
+                    if (i >= 1) {
+                        float nM[C], nI[C], nD[C];
+#pragma unroll
+                        for (int c = C - 1; c >= 0; c--) {
+                            const float m1 = (c < C - 1) ? mn[c + 1] : mnR;
+                            const float dr = (c < C - 1) ? nD[c + 1] : cDb;
+                            nD[c] = fmaf(m1, oDM[c], fmaf(dr, oDD[c], ebs));
+                            nM[c] = fmaf(m1, oMM[c], fmaf(sI[c], oMI[c], fmaf(dr, oMD[c], ebs)));
+                            nI[c] = fmaf(m1, oIM[c], sI[c] * oII[c]);
+                        }
+                        // posterior decoding against the stored forward row
+                        const float fac = exp2f((float)(gFarr[s * TT + tF] + g - gT)) * invT;
+                        float *fm = tM + ((size_t)tF * 32 + lane) * C, *fi = tI + ((size_t)tF * 32 + lane) * C;
+                        float FMv[C], FIv[C];
+                        if (C % 4 == 0) {
+#pragma unroll
+                            for (int v = 0; v < C / 4; v++) {
+                                float4 a = reinterpret_cast<const float4 *>(fm)[v], b = reinterpret_cast<const float4 *>(fi)[v];
+                                FMv[4 * v] = a.x; FMv[4 * v + 1] = a.y; FMv[4 * v + 2] = a.z; FMv[4 * v + 3] = a.w;
+                                FIv[4 * v] = b.x; FIv[4 * v + 1] = b.y; FIv[4 * v + 2] = b.z; FIv[4 * v + 3] = b.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < C; c++) { FMv[c] = fm[c]; FIv[c] = fi[c]; }
+                        }
+                        if (ALIGN) {
+                            float pM[C], pI[C];
+#pragma unroll
+                            for (int c = 0; c < C; c++) { pM[c] = FMv[c] * nM[c] * fac; pI[c] = FIv[c] * nI[c] * fac; }
+                            if (C % 4 == 0) {
+#pragma unroll
+                                for (int v = 0; v < C / 4; v++) {
+                                    reinterpret_cast<float4 *>(fm)[v] = make_float4(pM[4 * v], pM[4 * v + 1], pM[4 * v + 2], pM[4 * v + 3]);
+                                    reinterpret_cast<float4 *>(fi)[v] = make_float4(pI[4 * v], pI[4 * v + 1], pI[4 * v + 2], pI[4 * v + 3]);
+                                }
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < C; c++) { fm[c] = pM[c]; fi[c] = pI[c]; }
+                            }
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < C; c++) {
+                                accM[c] = fmaf(FMv[c] * nM[c], fac, accM[c]);
+                                accI = fmaf(FIv[c] * nI[c], fac, accI);
+                            }
+                        }
+#pragma unroll
+                        for (int c = 0; c < C; c++) { sM[c] = nM[c]; sI[c] = nI[c]; sD[c] = nD[c]; }
+                    }
+                    rMb = cMb;
+                    ebs *= ploop;
+                    if (lane == 0) {
+                        if (!firstS) { bndM[i] = sM[0]; bndD[i] = sD[0]; bndE[i] = bp; bndG[i] = g; }
+                        else {
+                            // N_b(i) = N_b(i+1)*loop + B_b(i)*move   (N_b(Ls) = 0)
+                            const float f = pow2i(xNg - g);
+                            xNv = (i == Ls) ? 0.f : xNv * f * ploop + bp * pmove;
+                            xNg = g;
+                            rNB[i] = xNv; rNBg[i] = g;
+                        }
+                    }
+                }
+                if ((tp & (W_SCALE_EVERY - 1)) == (W_SCALE_EVERY - 1)) {
+                    float mx = 0.f;
+#pragma unroll
+                    for (int c = 0; c < C; c++) mx = fmaxf(mx, fmaxf(sM[c], fmaxf(sI[c], sD[c])));
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
+                    int e_need = (mx > 1048576.f) ? fexp(mx) : 0;
+                    if (!lastS) {
+                        int ahead = bndG[max(0, Ls - (tp + W_SCALE_EVERY))] - 40 - g;
+                        e_need = max(e_need, ahead);
+                    }
+                    if (e_need > 0) {
+                        const float f = pow2i(-e_need);
+                        g += e_need;
+#pragma unroll
+                        for (int c = 0; c < C; c++) { sM[c] *= f; sI[c] *= f; sD[c] *= f; }
+                        rMb *= f; bp *= f; ebs *= f;
+                    }
+                }
+            }
+            if (!ALIGN) {
+                // null2 numerators: sum_k fM(k) * e_k(x) for the canonical symbols (rows 0..K-1 of the table)
+                const int K = (E.Kp == 29) ? 20 : 4;
+                for (int x = 0; x < K; x++) {
+                    float e[C];
+                    load_emis<C>(emis_strip + (size_t)x * Mstr, 32, lane, e);
+                    float v = 0.f;
+#pragma unroll
+                    for (int c = 0; c < C; c++) v = fmaf(accM[c], e[c], v);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+                    if (lane == 0) s_n2[w][x] += v;
+                }
+            }
+            if (firstS) { xNv = __shfl_sync(FULL, xNv, 0); xNg = __shfl_sync(FULL, xNg, 0); }
+            __syncwarp();
+        }
+        if (lane == 0 && Wk.dbg_bwd) Wk.dbg_bwd[it.pair] = logf(xNv) + (float)xNg * 0.69314718056f;
+
+        // N / C flank posteriors: ppN(i) = F_N(i-1) B_N(i) loop / T ; ppC(i) = F_C(i-1) B_C(i) loop / T
+        // F_N(i) = loop^i, B_C(i) = move * loop^(Ls-i)
+        float fX = 0.f;
+        {
+            const float l2loop = log2f(ploop), l2move = log2f(pmove), l2T = log2f(Tm) + (float)gT;
+            for (int base = 1; base <= Ls; base += 32) {
+                const int i = base + lane;
+                float pn = 0.f, pc = 0.f;
+                if (i <= Ls) {
+                    // ppN(i) = loop^(i-1) * N_b(i) * loop / T
+                    const float nb = rNB[i];
+                    pn = (nb > 0.f) ? exp2f((float)i * l2loop + log2f(nb) + (float)rNBg[i] - l2T) : 0.f;
+                    if (i >= 2) {
+                        const float fc = rFC[i - 1];
+                        pc = (fc > 0.f) ? exp2f(log2f(fc) + (float)rFCg[i - 1] + l2move + (float)(Ls - i + 1) * l2loop - l2T) : 0.f;
+                    }
+                    if (ALIGN) { rNOA[i] = pn; rPPC[i] = pc; }
+                }
+                fX += pn + pc;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) fX += __shfl_xor_sync(FULL, fX, o);
+        }
+
+        if (!ALIGN) {
+            // ---- null2 by expectation ----
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) accI += __shfl_xor_sync(FULL, accI, o);
+            __syncwarp();
+            const int K = (E.Kp == 29) ? 20 : 4;
+            const float norm = 1.0f / (float)Ls;
+            // log null2 per dense symbol, computed by lanes x < nsym
+            float ln2 = 0.f;
+            if (lane < Q.nsym) {
+                if (lane < K) ln2 = logf((s_n2[w][lane] + accI + fX) * norm);
+            }
+            __syncwarp();
+            if (lane < K) s_n2[w][lane] = (s_n2[w][lane] + accI + fX) * norm;
+            __syncwarp();
+            if (lane >= K && lane < Q.nsym) {
+                // degenerate symbol: unweighted mean of the canonical null2 odds over its members
+                const int code = Q.symrow[lane];
+                unsigned mask = 0;
+                if (E.Kp == 29) {  // amino: B=ND J=IL Z=QE O=K U=C X=all   (codes 21..26)
+                    const unsigned m[6] = {(1u << 11) | (1u << 2), (1u << 7) | (1u << 9), (1u << 13) | (1u << 3), 1u << 8, 1u << 1, 0xFFFFFu};
+                    mask = (code >= 21 && code <= 26) ? m[code - 21] : 0u;
+                } else {  // nucleic: R Y M K S W H B V D N (codes 5..15), bits A=1 C=2 G=4 T=8
+                    const unsigned m[11] = {5, 10, 3, 12, 6, 9, 11, 14, 7, 13, 15};
+                    mask = (code >= 5 && code <= 15) ? m[code - 5] : 0u;
+                }
+                float sum = 0.f; int cnt = 0;
+                for (int x = 0; x < K; x++) if (mask >> x & 1u) { sum += s_n2[w][x]; cnt++; }
+                ln2 = cnt ? logf(sum / (float)cnt) : 0.f;
+            }
+            // domain correction = sum over envelope residues of ln null2[x]
+            float dc = 0.f;
+            for (int base = 0; base < Ls; base += 32) {
+                const int p = base + lane;
+                const int xr = (p < Ls) ? dsq[p] : 0;
+                for (int z = 0; z < 32 && base + z < Ls; z++) {
+                    const int xx = __shfl_sync(FULL, xr, z);
+                    dc += __shfl_sync(FULL, ln2, xx);
+                }
+            }
+            if (lane == 0) { Wk.envsc[it.pair] = fwd_nats; Wk.domcorr[it.pair] = dc; }
+            __syncwarp();
+            continue;
+        }
+
+        // ======================================= Optimal accuracy (align mode) =======================================
+        if (ALIGN) {
+            __syncwarp();
+            // N_oa(i) = sum_{i'<=i} ppN(i') : in-place inclusive prefix sum over rNOA[1..Ls]; rNOA[0] = 0
+            {
+                float carry = 0.f;
+                if (lane == 0) rNOA[0] = 0.f;
+                for (int base = 1; base <= Ls; base += 32) {
+                    const int i = base + lane;
+                    float v = (i <= Ls) ? rNOA[i] : 0.f;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { float u = __shfl_up_sync(FULL, v, o); if (lane >= o) v += u; }
+                    v += carry;
+                    if (i <= Ls) rNOA[i] = v;
+                    carry = __shfl_sync(FULL, v, 31);
+                }
+            }
+            __syncwarp();
+            const float NEG = -INFINITY;
+            const int Qs = max(2, (Mh - 1) / 4 + 1);  // HMMER's striped segment count, for select_e tie order
+            for (int s = 0; s < nstrips; s++) {
+                const long long k0 = (long long)s * SW + lane * C;
+                float pa[C], pb[C], pg[C], pmd[C], pdd[C], pmi[C], pii[C], pen[C];
+                load_cols<C>(E.tMM + po, k0, pa); load_cols<C>(E.tIM + po, k0, pb); load_cols<C>(E.tDM + po, k0, pg);
+                load_cols<C>(E.tMD + po, k0, pmd); load_cols<C>(E.tDD + po, k0, pdd);
+                load_cols<C>(E.tMI + po, k0 + 1, pmi); load_cols<C>(E.tII + po, k0 + 1, pii);
+                load_cols<C>(E.entry + po, k0 + 1, pen);
+                float oM[C], oI[C], oD[C];
+#pragma unroll
+                for (int c = 0; c < C; c++) { oM[c] = NEG; oI[c] = NEG; oD[c] = NEG; }
+                float rM = NEG, rI = NEG, rD = NEG;
+                float eV = NEG; int eK = 0;  // running select_e candidate of the lane's last row: eK = k | isD<<30
+                const bool first = (s == 0), last = (s == nstrips - 1);
+                float *tM = tileM + (size_t)s * TT * SW, *tI = tileI + (size_t)s * TT * SW;
+                unsigned *tb = bits + (size_t)s * TT * 32;
+                for (int t = 1; t <= nsteps; t++) {
+                    const int i = t - lane;
+                    const bool act = (i >= 1 && i <= Ls);
+                    float cM = __shfl_up_sync(FULL, oM[C - 1], 1);
+                    float cI = __shfl_up_sync(FULL, oI[C - 1], 1);
+                    float cD = __shfl_up_sync(FULL, oD[C - 1], 1);
+                    float cEV = __shfl_up_sync(FULL, eV, 1);
+                    int cEK = __shfl_up_sync(FULL, eK, 1);
+                    if (lane == 0) {
+                        if (!first && act) { cM = bndM[i]; cI = bndI[i]; cD = bndD[i]; cEV = bndE[i]; cEK = bndG[i]; }
+                        else { cM = NEG; cI = NEG; cD = NEG; cEV = NEG; cEK = 0; }
+                    }
+                    if (act) {
+                        const float xB = rNOA[i - 1];
+                        const float *fm = tM + ((size_t)t * 32 + lane) * C, *fi = tI + ((size_t)t * 32 + lane) * C;
+                        float pM[C], pI[C];
+#pragma unroll
+                        for (int c = 0; c < C; c++) { pM[c] = fm[c]; pI[c] = fi[c]; }
+                        float nM[C], nI[C], nD[C];
+                        unsigned word = 0;
+#pragma unroll
+                        for (int c = C - 1; c >= 0; c--) {
+                            const float pm = c > 0 ? oM[c - 1] : rM, pi = c > 0 ? oI[c - 1] : rI, pd = c > 0 ? oD[c - 1] : rD;
+                            const long long kcol = k0 + 1 + c;
+                            const bool valid = kcol <= Mh;
+                            // DP value: zero-probability transitions contribute the constant 0.0 (HMMER's masking)
+                            float sv = pen[c] > 0.f ? xB : 0.f;
+                            sv = fmaxf(sv, pa[c] > 0.f ? pm : 0.f);
+                            sv = fmaxf(sv, pb[c] > 0.f ? pi : 0.f);
+                            sv = fmaxf(sv, pg[c] > 0.f ? pd : 0.f);
+                            nM[c] = valid ? sv + pM[c] : NEG;
+                            // traceback choice (select_m): order M, I, D, B; zero-probability transitions are -inf
+                            const float q0 = pa[c] != 0.f ? pm : NEG, q1 = pb[c] != 0.f ? pi : NEG,
+                                        q2 = pg[c] != 0.f ? pd : NEG, q3 = pen[c] != 0.f ? xB : NEG;
+                            int best = 0; float bv = q0;
+                            if (q1 > bv) { bv = q1; best = 1; }
+                            if (q2 > bv) { bv = q2; best = 2; }
+                            if (q3 > bv) { bv = q3; best = 3; }
+                            // I(i,k)
+                            float iv = pmi[c] > 0.f ? oM[c] : 0.f;
+                            iv = fmaxf(iv, pii[c] > 0.f ? oI[c] : 0.f);
+                            nI[c] = (valid && kcol < Mh) ? iv + pI[c] : NEG;
+                            const float i0v = pmi[c] != 0.f ? oM[c] : NEG, i1v = pii[c] != 0.f ? oI[c] : NEG;
+                            const int ibit = (i1v > i0v) ? 1 : 0;
+                            word |= ((unsigned)best | ((unsigned)ibit << 2)) << (4 * c);
+                        }
+#pragma unroll
+                        for (int c = 0; c < C; c++) {
+                            const float ml = c > 0 ? nM[c - 1] : cM, dlv = c > 0 ? nD[c - 1] : cD;
+                            const long long kcol = k0 + 1 + c;
+                            float dv = pmd[c] > 0.f ? ml : 0.f;
+                            dv = fmaxf(dv, pdd[c] > 0.f ? dlv : 0.f);
+                            nD[c] = (kcol >= 2 && kcol <= Mh) ? dv : NEG;
+                            const float d0 = pmd[c] != 0.f ? ml : NEG, d1 = pdd[c] != 0.f ? dlv : NEG;
+                            word |= ((d1 > d0) ? 8u : 0u) << (4 * c);
+                        }
+                        tb[(size_t)t * 32 + lane] = word;
+                        // select_e candidates
+                        float bV = cEV; int bK = cEK;
+#pragma unroll
+                        for (int c = 0; c < C; c++) {
+                            const int kcol = (int)(k0 + 1 + c);
+                            if (kcol <= Mh) {
+                                const int ord = ((kcol - 1) % Qs) * 4 + (kcol - 1) / Qs;
+                                const int bord = (((bK & 0x3fffffff) - 1) % Qs) * 4 + ((bK & 0x3fffffff) - 1) / Qs;
+                                if ((bK & 0x3fffffff) == 0 || oa_e_better(nM[c], 0, ord, bV, bK >> 30, bord)) { bV = nM[c]; bK = kcol; }
+                                const int bord2 = (((bK & 0x3fffffff) - 1) % Qs) * 4 + ((bK & 0x3fffffff) - 1) / Qs;
+                                if (oa_e_better(nD[c], 1, ord, bV, bK >> 30, bord2)) { bV = nD[c]; bK = kcol | (1 << 30); }
+                            }
+                        }
+                        eV = bV; eK = bK;
+#pragma unroll
+                        for (int c = 0; c < C; c++) { oM[c] = nM[c]; oI[c] = nI[c]; oD[c] = nD[c]; }
+                        rM = cM; rI = cI; rD = cD;
+                        if (lane == 31) {
+                            if (!last) { bndM[i] = oM[C - 1]; bndI[i] = oI[C - 1]; bndD[i] = oD[C - 1]; bndE[i] = eV; bndG[i] = eK; }
+                            else { rEOA[i] = eV; rKE[i] = eK; }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            __syncwarp();
+            // ---- traceback (lane 0; SURVEY 8a "Align semantics" item 4) ----
+            {
+                int *colsw = Wk.cols + Wk.col_off[it.pair];
+                for (int z = lane; z < Ls; z += 32) colsw[z] = -1;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                int *cols = Wk.cols + Wk.col_off[it.pair];
+                // C_oa(i) = max(C_oa(i-1) + ppC(i), E_oa(i)); C_oa(0) = -inf : computed forward into rFC (reuse)
+                float c = NEG;
+                for (int i = 1; i <= Ls; i++) {
+                    float a = c + rPPC[i];
+                    float e = rEOA[i];
+                    c = fmaxf(a, e);
+                    rFC[i] = c;
+                }
+                rFC[0] = NEG;
+                int i = Ls, k = 0, st = 4;  // 0=M 1=I 2=D 3=B 4=C 5=E
+                int guard = 2 * (Ls + Mh) + 8;  // a valid trace never needs more steps
+                while (st != 3 && guard-- > 0) {
+                    if (st != 4 && st != 5 && (k < 1 || i < 1 || k > Mh)) break;
+                    if (st == 4) {
+                        if (i == 0) break;
+                        const float a = rFC[i - 1] + rPPC[i], e = rEOA[i];
+                        if (a >= e) i--; else st = 5;
+                    } else if (st == 5) {
+                        const int ke = rKE[i];
+                        k = ke & 0x3fffffff; st = (ke >> 30) ? 2 : 0;
+                    } else {
+                        const int s = (k - 1) / SW, r = (k - 1) - s * SW, l = r / C, cc = r - l * C;
+                        const unsigned wd = bits[((size_t)s * TT + (i + l)) * 32 + l] >> (4 * cc);
+                        if (st == 0) { cols[i - 1] = k - 1; st = (int)(wd & 3u); k--; i--; }
+                        else if (st == 2) { st = (wd & 8u) ? 2 : 0; k--; }
+                        else { st = (wd & 4u) ? 1 : 0; i--; }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+}  // namespace witch

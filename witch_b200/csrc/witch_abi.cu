@@ -1,0 +1,320 @@
+// C ABI of libwitch_b200.so (see include/witch_b200.h). Host orchestration + kernel launches.
+#include "../../include/witch_b200.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <numeric>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "device_types.cuh"
+#include "hmm_profile.h"
+#include "parser_kernel.cuh"
+#include "wave_kernels.cuh"
+#include "post_kernels.cuh"
+
+using namespace witch;
+
+// ----------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{0};
+static bool g_prof = false;
+struct ProfAcc { double ms = 0, cells = 0; uint64_t launches = 0; };
+static ProfAcc g_acc[3];
+
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define CUDA_TRY(x)                                                                                          \
+    do {                                                                                                     \
+        cudaError_t e_ = (x);                                                                                \
+        if (e_ != cudaSuccess)                                                                               \
+            throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #x);      \
+    } while (0)
+
+struct ScopedTimer {  // CUDA-event timing of a group of launches on `st` (only when profiling is enabled)
+    cudaEvent_t a = nullptr, b = nullptr;
+    cudaStream_t st;
+    int which;
+    double cells;
+    uint64_t n0;
+    ScopedTimer(int which_, cudaStream_t st_, double cells_) : st(st_), which(which_), cells(cells_) {
+        n0 = g_launches.load();
+        if (g_prof) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
+    }
+    ~ScopedTimer() {
+        if (!g_prof || !a) return;
+        cudaEventRecord(b, st);
+        cudaEventSynchronize(b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        g_acc[which].ms += ms; g_acc[which].cells += cells; g_acc[which].launches += g_launches.load() - n0;
+        cudaEventDestroy(a); cudaEventDestroy(b);
+    }
+};
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    void alloc(size_t n_) {
+        if (n_ <= n && p) return;
+        release();
+        n = n_;
+        CUDA_TRY(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    }
+    void upload(const std::vector<T> &v, cudaStream_t st = nullptr) {
+        alloc(v.size());
+        if (!v.empty()) CUDA_TRY(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    ~DevBuf() { release(); }
+};
+
+struct witch_ehmm {
+    int device = 0, H = 0, alph = 0, Kp = 0, num_sms = 148;
+    std::vector<int> M, nseq, stride;
+    std::vector<long long> poff, eoff;
+    DevBuf<float> tMM, tMI, tMD, tIM, tII, tDM, tDD, entry, emis;
+    DevBuf<int> dM, dstride, dnseq;
+    DevBuf<long long> dpoff, deoff;
+    // reusable workspaces
+    DevBuf<float> scratch, f1, f2;
+    DevBuf<unsigned> counter;
+    DevBuf<int> i1, i2, i3;
+    DevBuf<PairParse> parse;
+    DevBuf<uint8_t> bytes;
+    DevEhmm view() const {
+        DevEhmm v;
+        v.tMM = tMM.p; v.tMI = tMI.p; v.tMD = tMD.p; v.tIM = tIM.p; v.tII = tII.p; v.tDM = tDM.p; v.tDD = tDD.p;
+        v.entry = entry.p; v.emis = emis.p; v.M = dM.p; v.stride = dstride.p; v.poff = dpoff.p; v.eoff = deoff.p;
+        v.H = H; v.Kp = Kp;
+        return v;
+    }
+};
+
+struct witch_queries {
+    int device = 0, n = 0, nsym = 0, alph = 0;
+    std::vector<int> len;
+    std::vector<long long> off;
+    int symrow[MAX_SYM];
+    int maxlen = 0;
+    long long total = 0;
+    DevBuf<uint8_t> dsq;
+    DevBuf<long long> doff;
+    DevBuf<int> dlen;
+    DevQueries view() const {
+        DevQueries v;
+        v.dsq = dsq.p; v.off = doff.p; v.len = dlen.p; v.n = n; v.nsym = nsym;
+        for (int i = 0; i < MAX_SYM; i++) v.symrow[i] = symrow[i];
+        return v;
+    }
+};
+
+// ----------------------------------------------------------------------------------------------------------
+extern "C" const char *witch_last_error(void) { return g_err.c_str(); }
+extern "C" const char *witch_version(void) { return "witch_b200 0.1.0 sm_100a"; }
+extern "C" int witch_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+extern "C" uint64_t witch_kernel_launches(void) { return g_launches.load(); }
+extern "C" void witch_prof_enable(int on) { g_prof = on != 0; }
+extern "C" void witch_prof_reset(void) { for (auto &a : g_acc) a = ProfAcc(); }
+extern "C" double witch_prof_get(int which, double *cells, uint64_t *launches) {
+    if (which < 0 || which > 2) return 0;
+    if (cells) *cells = g_acc[which].cells;
+    if (launches) *launches = g_acc[which].launches;
+    return g_acc[which].ms;
+}
+
+static void require_device() {
+    if (witch_device_count() <= 0) throw std::runtime_error("no CUDA device available (witch_b200 has no CPU fallback)");
+}
+
+extern "C" int witch_ehmm_create(int n_hmm, const char *const *paths, witch_ehmm **out) {
+    if (n_hmm <= 0 || !paths || !out) return fail(WITCH_ERR_ARG, "witch_ehmm_create: bad arguments");
+    witch_ehmm *e = nullptr;
+    try {
+        std::vector<HostProfile> ps;
+        ps.reserve(n_hmm);
+        for (int h = 0; h < n_hmm; h++) {
+            try { ps.push_back(load_profile(paths[h], 0)); }
+            catch (const std::exception &ex) { return fail(WITCH_ERR_IO, ex.what()); }
+            if (ps[h].alph != ps[0].alph) return fail(WITCH_ERR_ARG, "profiles use different alphabets");
+        }
+        require_device();
+        e = new witch_ehmm();
+        CUDA_TRY(cudaGetDevice(&e->device));
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, e->device));
+        e->num_sms = prop.multiProcessorCount;
+        e->H = n_hmm; e->alph = ps[0].alph; e->Kp = alphabet_info(e->alph).Kp;
+        long long po = 0, eo = 0;
+        for (auto &p : ps) {
+            e->M.push_back(p.M); e->nseq.push_back(p.nseq); e->stride.push_back(p.stride);
+            e->poff.push_back(po); e->eoff.push_back(eo);
+            po += p.stride; eo += (long long)e->Kp * p.stride;
+        }
+        auto cat = [&](std::vector<float> HostProfile::*f) {
+            std::vector<float> v; v.reserve(po);
+            for (auto &p : ps) v.insert(v.end(), (p.*f).begin(), (p.*f).end());
+            return v;
+        };
+        e->tMM.upload(cat(&HostProfile::tMM)); e->tMI.upload(cat(&HostProfile::tMI));
+        e->tMD.upload(cat(&HostProfile::tMD)); e->tIM.upload(cat(&HostProfile::tIM));
+        e->tII.upload(cat(&HostProfile::tII)); e->tDM.upload(cat(&HostProfile::tDM));
+        e->tDD.upload(cat(&HostProfile::tDD)); e->entry.upload(cat(&HostProfile::entry));
+        e->emis.upload(cat(&HostProfile::emis));
+        e->dM.upload(e->M); e->dstride.upload(e->stride); e->dnseq.upload(e->nseq);
+        e->dpoff.upload(e->poff); e->deoff.upload(e->eoff);
+        CUDA_TRY(cudaDeviceSynchronize());
+        *out = e;
+        return WITCH_OK;
+    } catch (const std::exception &ex) {
+        delete e;
+        return fail(WITCH_ERR_CUDA, ex.what());
+    }
+}
+extern "C" void witch_ehmm_destroy(witch_ehmm *e) { delete e; }
+extern "C" int witch_ehmm_count(const witch_ehmm *e) { return e ? e->H : 0; }
+extern "C" int witch_ehmm_alphabet(const witch_ehmm *e) { return e ? e->alph : -1; }
+extern "C" int witch_ehmm_info(const witch_ehmm *e, int32_t *M, int32_t *nseq) {
+    if (!e) return fail(WITCH_ERR_ARG, "null handle");
+    for (int h = 0; h < e->H; h++) { if (M) M[h] = e->M[h]; if (nseq) nseq[h] = e->nseq[h]; }
+    return WITCH_OK;
+}
+
+extern "C" int witch_queries_create(const witch_ehmm *e, int n, const char *residues, const int64_t *offsets,
+                                    witch_queries **out) {
+    if (!e || n < 0 || !offsets || !out || (n > 0 && !residues)) return fail(WITCH_ERR_ARG, "witch_queries_create: bad arguments");
+    witch_queries *q = nullptr;
+    try {
+        const AlphabetInfo &A = alphabet_info(e->alph);
+        q = new witch_queries();
+        q->n = n; q->alph = e->alph; q->device = e->device;
+        const long long total = offsets[n];
+        std::vector<uint8_t> codes((size_t)total);
+        int dense[64];
+        for (int i = 0; i < 64; i++) dense[i] = -1;
+        q->nsym = 0;
+        for (int x = 0; x < A.K; x++) { dense[x] = q->nsym; q->symrow[q->nsym++] = x; }  // canonical rows first
+        for (int i = 0; i < n; i++) {
+            if (offsets[i + 1] < offsets[i]) { delete q; return fail(WITCH_ERR_ARG, "offsets not monotone"); }
+            q->len.push_back((int)(offsets[i + 1] - offsets[i]));
+            q->off.push_back(offsets[i]);
+            q->maxlen = std::max(q->maxlen, q->len.back());
+        }
+        q->off.push_back(total);
+        q->total = total;
+        for (long long p = 0; p < total; p++) {
+            int c = A.code[(unsigned char)residues[p]];
+            if (c < 0 || c == A.K || c >= A.Kp - 2) {  // invalid char, gap, '*' or '~' inside an unaligned query
+                delete q;
+                return fail(WITCH_ERR_ARG, std::string("invalid residue '") + residues[p] + "' in query");
+            }
+            if (dense[c] < 0) {
+                if (q->nsym >= MAX_SYM) { delete q; return fail(WITCH_ERR_LIMIT, "too many distinct symbols"); }
+                dense[c] = q->nsym; q->symrow[q->nsym++] = c;
+            }
+            codes[(size_t)p] = (uint8_t)dense[c];
+        }
+        for (int i = q->nsym; i < MAX_SYM; i++) q->symrow[i] = 0;
+        require_device();
+        q->dsq.upload(codes); q->doff.upload(q->off); q->dlen.upload(q->len);
+        CUDA_TRY(cudaDeviceSynchronize());
+        *out = q;
+        return WITCH_OK;
+    } catch (const std::exception &ex) {
+        delete q;
+        return fail(WITCH_ERR_CUDA, ex.what());
+    }
+}
+extern "C" void witch_queries_destroy(witch_queries *q) { delete q; }
+extern "C" int witch_queries_count(const witch_queries *q) { return q ? q->n : 0; }
+
+// ----------------------------------------------------------------------------------------------------------
+// Family S launch plumbing
+struct SClass { int C, T; std::vector<int> hmms; };
+
+static std::vector<SClass> s_classes(const witch_ehmm *e, const std::vector<int> &hmms) {
+    std::map<std::pair<int, int>, std::vector<int>> m;
+    for (int h : hmms) {
+        const int M = e->M[h];
+        if (M > 3840) throw std::runtime_error("model longer than 3840 nodes is not supported yet");
+        int C = (M <= 1024) ? 4 : (M <= 3072) ? 8 : 12;
+        int T = ((M + C - 1) / C + 31) / 32 * 32;
+        if (T < 64) T = 64;
+        m[{C, T}].push_back(h);
+    }
+    std::vector<SClass> out;
+    for (auto &kv : m) out.push_back({kv.first.first, kv.first.second, kv.second});
+    return out;
+}
+
+template <int C>
+static void launch_parser(const witch_ehmm *e, const witch_queries *q, int T, ParserWork wk, cudaStream_t st) {
+    const size_t smem = ((size_t)q->nsym * T * C + 9 * S_RED) * sizeof(float);
+    if (smem > 200 * 1024) throw std::runtime_error("emission table does not fit shared memory (too many symbols x model length)");
+    CUDA_TRY(cudaFuncSetAttribute(mh_parser_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mh_parser_kernel<C>, T, smem));
+    if (occ < 1) throw std::runtime_error("parser kernel cannot be resident (registers/shared memory)");
+    const long long nitems = (long long)wk.nh * wk.nq;
+    const int grid = (int)std::min<long long>(nitems, (long long)e->num_sms * occ);
+    mh_parser_kernel<C><<<grid, T, smem, st>>>(e->view(), q->view(), wk);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+}
+
+// Runs the multihit parser for all (query in qsel) x (hmm in hsel); results in e->parse [n_queries*H].
+static void run_parser(witch_ehmm *e, witch_queries *q, const std::vector<int> &qsel, const std::vector<int> &hsel,
+                       float *d_dbg_bwd, cudaStream_t st) {
+    if (qsel.empty() || hsel.empty()) return;
+    std::vector<int> qorder(qsel);
+    std::stable_sort(qorder.begin(), qorder.end(), [&](int a, int b) { return q->len[a] > q->len[b]; });
+    e->parse.alloc((size_t)q->n * e->H);
+    e->i1.upload(qorder, st);
+    const int Lcap = q->maxlen + 1;
+    int maxgrid = e->num_sms * 8;
+    e->scratch.alloc((size_t)maxgrid * 11 * (Lcap + 1));
+    e->counter.alloc(64);
+    auto classes = s_classes(e, hsel);
+    std::vector<int> allh;
+    std::vector<int> hoff;
+    for (auto &c : classes) {
+        std::stable_sort(c.hmms.begin(), c.hmms.end(), [&](int a, int b) { return e->M[a] > e->M[b]; });
+        hoff.push_back((int)allh.size());
+        allh.insert(allh.end(), c.hmms.begin(), c.hmms.end());
+    }
+    e->i2.upload(allh, st);
+    CUDA_TRY(cudaMemsetAsync(e->counter.p, 0, 64 * sizeof(unsigned), st));
+    double cells = 0;
+    {
+        double sl = 0, sm = 0;
+        for (int x : qsel) sl += q->len[x];
+        for (int h : hsel) sm += e->M[h];
+        cells = sl * sm;
+    }
+    ScopedTimer tm(0, st, cells);
+    for (size_t ci = 0; ci < classes.size(); ci++) {
+        if (ci >= 64) throw std::runtime_error("too many launch classes");
+        ParserWork wk;
+        wk.hmms = e->i2.p + hoff[ci]; wk.nh = (int)classes[ci].hmms.size();
+        wk.qorder = e->i1.p; wk.nq = (int)qorder.size();
+        wk.Lcap = Lcap; wk.scratch = e->scratch.p; wk.counter = e->counter.p + ci; wk.out = e->parse.p;
+        wk.dbg_bwd = d_dbg_bwd;
+        switch (classes[ci].C) {
+            case 4: launch_parser<4>(e, q, classes[ci].T, wk, st); break;
+            case 8: launch_parser<8>(e, q, classes[ci].T, wk, st); break;
+            case 12: launch_parser<12>(e, q, classes[ci].T, wk, st); break;
+            default: throw std::runtime_error("bad class");
+        }
+    }
+}
+
+#include "abi_stages.inl"
