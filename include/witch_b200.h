@@ -125,6 +125,11 @@ void witch_prof_reset(void);
  * Returns accumulated ms and (via *cells) the DP cells those launches covered. */
 double witch_prof_get(int which, double *cells, uint64_t *launches);
 
+/* Measured FP32 FMA throughput of the current device in TFLOP/s (2 flop per FMA lane-op): a dependent-chain-free
+ * FFMA micro-benchmark run for roughly `ms` milliseconds. This is the ALU roofline denominator bench.py reports
+ * (MEASURED_PEAKS.json carries no CUDA-core figure). Returns a negative value on error. */
+double witch_measure_fp32_peak(double ms);
+
 /* Debug / test hooks (stable, used by tests/): plain Forward and Backward scores in nats for n_pairs pairs.
  * mode: 1 = multihit local (hmmsearch parser), 0 = unihit local (hmmalign / envelope). HOST arrays. */
 int witch_debug_fwdbwd(witch_ehmm *e, witch_queries *q, int n_pairs, const int32_t *qidx, const int32_t *hidx,

@@ -1,0 +1,208 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the oracle and the reference binaries' golden
+vectors. Tolerances (BASELINE.json north_star): bit scores within 0.01 bits of the float64 oracle; identical
+reported sets; identical top-k HMM ranking and weights (1e-12 relative, the reference's own float64 summation-order
+noise); alignment columns bit-exact except on documented float near-ties (<= 1 residue in 2000)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from golden_util import SETS, load_set
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+pytestmark = pytest.mark.gpu
+
+SCORE_TOL_BITS = 0.01
+
+
+@pytest.fixture(scope="module")
+def wb():
+    import witch_b200
+    from witch_b200 import _lib
+    assert _lib.load().witch_device_count() > 0, "CUDA library loaded but no device: no CPU fallback exists"
+    return witch_b200
+
+
+def _oracle_scores(profs, queries):
+    out = {}
+    for qi, (_, s) in enumerate(queries):
+        for h, p in enumerate(profs):
+            out[(qi, h)] = O.score_pair(p, p.abc.digitize(s))
+    return out
+
+
+@pytest.mark.parametrize("setname", SETS)
+def test_scores_weights_columns_vs_oracle_and_golden(wb, setname, tmp_path):
+    gold, queries, paths = load_set(setname, str(tmp_path))
+    profs = [O.Profile(p) for p in paths]
+    E = wb.EHMM(paths)
+    Q = wb.Queries(E, [s for _, s in queries])
+    assert list(E.M) == [h["M"] for h in gold["hmms"]] and list(E.nseq) == [h["nseq"] for h in gold["hmms"]]
+    sc, rep, pre, fl = wb.score(E, Q)
+    ora = _oracle_scores(profs, queries)
+    for (qi, h), r in ora.items():
+        assert bool(rep[qi, h]) == r["reported"], (setname, qi, h, r)
+        assert abs(pre[qi, h] - r["pre_score"]) < SCORE_TOL_BITS
+        assert (fl[qi, h] & 1) == (r["flags"] & 1)
+        if r["reported"]:
+            assert abs(sc[qi, h] - r["score"]) < SCORE_TOL_BITS, (setname, qi, h, sc[qi, h], r)
+        else:
+            assert np.isnan(sc[qi, h])
+    # printed 1-decimal scores against the reference binary (non multi-domain pairs; values within 1e-3 of a
+    # rounding boundary may legitimately print differently)
+    names = [n for n, _ in queries]
+    nprint = 0
+    for h, hg in enumerate(gold["hmms"]):
+        for n, hit in hg["hits"].items():
+            qi = names.index(n)
+            if fl[qi, h] & 1 or not rep[qi, h]:
+                continue
+            x = float(sc[qi, h]) * 10.0
+            if abs(x - np.floor(x) - 0.5) < 0.01:
+                continue
+            assert O.printed_score(float(sc[qi, h])) == hit["score"], (setname, n, h, sc[qi, h], hit)
+            nprint += 1
+    assert nprint > 0
+    # weights / top-k
+    idx, w, cnt = wb.weights_topk(E, sc, rep, 10, 1)
+    for qi in range(Q.n):
+        ss = {h: O.printed_score(float(sc[qi, h])) for h in range(E.n) if rep[qi, h]}
+        if not ss:
+            assert cnt[qi] == 0 and (idx[qi] == -1).all()
+            continue
+        ranked = O.rank_bitscores(ss)
+        ow = O.calculate_weights([h for h, _ in ranked], [x for _, x in ranked], [int(E.nseq[h]) for h, _ in ranked], 10)
+        assert cnt[qi] == len(ow)
+        got = [(int(idx[qi, j]), float(w[qi, j])) for j in range(cnt[qi])]
+        for (gi, gw), (oi, owt) in zip(got, ow):
+            assert abs(gw - owt) <= 1e-12 * owt + 1e-300
+        assert sorted(i for i, _ in got) == sorted(i for i, _ in ow)
+        assert abs(sum(x for _, x in got) - 1.0) < 1e-9 or len(ss) > 10
+    # alignment columns against hmmalign's (golden) and the oracle's
+    pq, ph, exp = [], [], []
+    for h, hg in enumerate(gold["hmms"]):
+        for n, cols in hg["columns"].items():
+            pq.append(names.index(n)); ph.append(h); exp.append(np.array(cols, dtype=np.int32))
+    got = wb.align(E, Q, pq, ph)
+    nres = nbad = 0
+    for a, b in zip(got, exp):
+        assert len(a) == len(b)
+        nres += len(b); nbad += int((a != b).sum())
+    assert nbad <= nres // 2000, (setname, nbad, nres)
+
+
+def test_edge_cases(wb, tmp_path):
+    gold, queries, paths = load_set("dna_small", str(tmp_path))
+    E = wb.EHMM(paths)
+    prof = O.Profile(paths[0])
+    base = queries[0][1]
+    seqs = ["", "A", "ACGT", base, base.lower(), base[:50] + "NNNRYK" + base[50:], base, "T" * 300]
+    Q = wb.Queries(E, seqs)
+    sc, rep, pre, fl = wb.score(E, Q)
+    assert not rep[0].any() and np.isnan(sc[0]).all()          # empty query: never reported
+    assert np.array_equal(rep[3], rep[4]) and np.allclose(sc[3], sc[4], equal_nan=True)  # case-insensitive
+    assert np.allclose(sc[3], sc[6], equal_nan=True)            # duplicates score identically
+    for qi in (1, 2, 5, 7):
+        r = O.score_pair(prof, prof.abc.digitize(seqs[qi]))
+        assert bool(rep[qi, 0]) == r["reported"]
+        if r["reported"]:
+            assert abs(sc[qi, 0] - r["score"]) < SCORE_TOL_BITS
+    cols = wb.align(E, Q, [0, 1, 5, 3], [0, 0, 0, 1])
+    assert len(cols[0]) == 0 and len(cols[1]) == 1
+    ref = O.align_pair(prof, prof.abc.digitize(seqs[5]))
+    assert np.array_equal(cols[2], ref)
+    with pytest.raises(wb.WitchError):
+        wb.Queries(E, ["AC-GT"])       # gaps are not valid in unaligned queries
+    with pytest.raises(wb.WitchError):
+        wb.align(E, Q, [99], [0])      # pair index out of range
+
+
+def test_properties_at_scale(wb, tmp_path):
+    """Size-independent properties on a workload the oracle could not finish quickly."""
+    import synth
+    wl = synth.make_workload(str(tmp_path), alphabet="dna", n_total=1500, n_backbone=200, root_len=900, decomp=10,
+                             frag_frac=0.5, frag_mean=300, seed=11)
+    E = wb.EHMM(wl["hmm_paths"])
+    seqs = wl["seqs"][:600]
+    Q = wb.Queries(E, seqs)
+    sc, rep, pre, fl = wb.score(E, Q)
+    # (1) Forward == Backward totals for both the multihit and unihit engines
+    rng = np.random.default_rng(0)
+    pq = rng.integers(0, Q.n, 300).astype(np.int32)
+    ph = rng.integers(0, E.n, 300).astype(np.int32)
+    for mh in (True, False):
+        f, b = wb.debug_fwdbwd(E, Q, pq, ph, mh)
+        assert np.all(np.abs(f - b) < 2e-3 + 2e-6 * np.abs(f)), np.abs(f - b).max()
+    # (2) permutation invariance: scoring a shuffled query set gives the same numbers
+    perm = rng.permutation(Q.n)
+    Q2 = wb.Queries(E, [seqs[i] for i in perm])
+    sc2, rep2, _, _ = wb.score(E, Q2)
+    assert np.array_equal(rep2, rep[perm]) and np.allclose(sc2, sc[perm], equal_nan=True, atol=1e-5)
+    # (3) every query is reported by the root HMM (it contains the whole backbone) and weights sum to one
+    assert rep[:, 0].mean() > 0.99
+    idx, w, cnt = wb.weights_topk(E, sc, rep, 10, 1)
+    full = cnt == 10
+    assert np.all(w.sum(1)[~full & (cnt > 0)] > 1 - 1e-9) and np.all(w.sum(1) <= 1 + 1e-9)
+    assert np.all(np.diff(w, axis=1) <= 1e-18)
+    # (4) alignment columns are strictly increasing over matched residues and inside the model
+    keep = np.minimum(cnt, 2)
+    aq = np.repeat(np.arange(Q.n), keep).astype(np.int32)[:800]
+    ah = np.concatenate([idx[q, :keep[q]] for q in range(Q.n)]).astype(np.int32)[:800]
+    cols = wb.align(E, Q, aq, ah)
+    for c, q, h in zip(cols, aq, ah):
+        m = c[c >= 0]
+        assert len(c) == len(seqs[q]) and np.all(np.diff(m) > 0) and (len(m) == 0 or m[-1] < E.M[h])
+    # (5) spot-check against the oracle
+    for z in rng.integers(0, len(aq), 12):
+        p = O.Profile(wl["hmm_paths"][ah[z]])
+        d = p.abc.digitize(seqs[aq[z]])
+        r = O.score_pair(p, d)
+        assert abs(sc[aq[z], ah[z]] - r["score"]) < SCORE_TOL_BITS
+        assert (cols[z] != O.align_pair(p, d)).sum() <= 1
+
+
+def test_mirror_interface_end_to_end(wb, tmp_path):
+    """BatchedSearch mirrors the reference's function contracts (types and content)."""
+    from witch_b200.gcmm import BatchedSearch
+    gold, queries, paths = load_set("dna_small", str(tmp_path))
+    bs = BatchedSearch(paths, num_hmms=10)
+    bs.search([n for n, _ in queries], [s for _, s in queries])
+    ranked = bs.rankBitscores()
+    t2w = bs.writeWeights()
+    bb = bs.getBackbones(t2w)
+    names = [n for n, _ in queries]
+    for h, hg in enumerate(gold["hmms"]):
+        res = bs.hmmsearch_results(h)
+        for n, hit in hg["hits"].items():
+            if n in res and not (bs.flags[names.index(n), h] & 1):
+                assert abs(res[n][1] - hit["score"]) <= 0.1 + 1e-9
+    for t, sw in t2w.items():
+        assert isinstance(sw, tuple) and all(isinstance(i, int) and isinstance(x, float) for i, x in sw)
+        assert [x[1] for x in ranked[t]] == sorted((x[1] for x in ranked[t]), reverse=True)
+        log, wmap, s2c = bb[t]
+        assert log.startswith(t + "\tpassed to main pipeline with top ")
+        for h, cols in s2c.items():
+            assert len(cols) == len(dict(queries)[t]) and h in wmap
+            if t in gold["hmms"][h]["columns"]:
+                assert sum(a != b for a, b in zip(cols, gold["hmms"][h]["columns"][t])) <= 2
+
+
+def test_device_pipeline_matches_staged_calls(wb, tmp_path):
+    import torch
+    from witch_b200.gcmm import DevicePipeline
+    gold, queries, paths = load_set("amino_small", str(tmp_path))
+    E = wb.EHMM(paths)
+    Q = wb.Queries(E, [s for _, s in queries])
+    res = DevicePipeline(E, k=10).run(Q)
+    torch.cuda.synchronize()
+    sc, rep, _, _ = wb.score(E, Q)
+    assert np.allclose(res["scores"].cpu().numpy(), sc, equal_nan=True)
+    idx, w, cnt = wb.weights_topk(E, sc, rep, 10, 1)
+    assert np.array_equal(res["idx"].cpu().numpy(), idx) and np.allclose(res["w"].cpu().numpy(), w)
+    cols = wb.align(E, Q, res["pair_q"], res["pair_h"])
+    flat = res["cols"].cpu().numpy()
+    for p, c in enumerate(cols):
+        assert np.array_equal(flat[res["col_off"][p]:res["col_off"][p + 1]], c)

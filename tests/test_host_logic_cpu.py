@@ -1,0 +1,94 @@
+"""CPU: host-side logic of the mirror interface (witch_b200/gcmm.py, sharding) and the synthetic generator."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+from oracle import oracle as O
+from witch_b200 import gcmm, sharding
+
+
+def test_adaptive_inclusion_counts_matches_reference_loop():
+    rng = np.random.default_rng(3)
+    n, k = 200, 10
+    w = np.sort(rng.dirichlet(np.full(k, 0.2), n), axis=1)[:, ::-1].copy()
+    cnt = rng.integers(0, k + 1, n).astype(np.int32)
+    for q in range(n):
+        w[q, cnt[q]:] = 0
+    keep = gcmm.adaptive_inclusion_counts(w, cnt)
+    for q in range(n):
+        sw = [(j, w[q, j]) for j in range(cnt[q])]
+        assert keep[q] == len(O.adaptive_inclusion(sw))
+
+
+def test_write_weights_to_local_roundtrip(tmp_path):
+    t2w = {"A": ((3, 0.75), (1, 0.25)), "B": ((0, 1.0),)}
+    p = tmp_path / "weights.txt"
+    gcmm.writeWeightsToLocal(t2w, str(p))
+    back = {}
+    for ln in open(p):  # the reference's readWeightsFromLocal (weighting.py:184-194)
+        taxon, tw = ln.split(":")
+        back[taxon] = eval(tw)
+    assert back == t2w
+
+
+def test_partition_balances_cells_and_covers_everything():
+    rng = np.random.default_rng(0)
+    lengths = rng.integers(80, 1600, 5000)
+    for world in (1, 2, 3, 8):
+        parts = [sharding.partition_queries(lengths, r, world) for r in range(world)]
+        allq = np.sort(np.concatenate(parts))
+        assert np.array_equal(allq, np.arange(len(lengths)))
+        loads = np.array([lengths[p].sum() for p in parts], dtype=np.float64)
+        assert loads.max() / loads.mean() < 1.02
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n, k = 101, 4
+        lengths = np.arange(n) % 7 + 1
+        mine = sharding.partition_queries(lengths, rank, world)
+        idx = np.full((len(mine), k), -1, np.int32)
+        w = np.zeros((len(mine), k))
+        cnt = np.zeros(len(mine), np.int32)
+        for j, qq in enumerate(mine):  # fake per-query records that encode the global query id
+            idx[j, 0] = qq; w[j, 0] = qq / 1000.0; cnt[j] = 1
+        gi, gw, gc = sharding.gather_topk(idx, w, cnt, mine, n, device="cpu")
+        ok = bool((gi[:, 0] == np.arange(n)).all() and np.allclose(gw[:, 0], np.arange(n) / 1000.0) and (gc == 1).all())
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_topk_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_synthetic_workload_is_seeded_and_consistent(tmp_path):
+    import synth
+    a = synth.make_workload(str(tmp_path), **synth.CONFIGS["tiny"])
+    b = synth.make_workload(str(tmp_path), **synth.CONFIGS["tiny"])
+    assert a["seqs"] == b["seqs"] and a["hmm_paths"] == b["hmm_paths"]
+    prof = O.Profile(a["hmm_paths"][0])
+    assert prof.M == len(a["retained_columns"][0]) == a["backbone_length"] or prof.M <= a["backbone_length"]
+    assert prof.nseq == a["nseq"][0]
+    r = O.score_pair(prof, prof.abc.digitize(a["seqs"][0]))
+    assert r["reported"] and r["score"] > 10

@@ -35,6 +35,7 @@ SYMBOLS = {
     "witch_prof_enable": (None, [ctypes.c_int]),
     "witch_prof_reset": (None, []),
     "witch_prof_get": (ctypes.c_double, [ctypes.c_int, c_f64p, c_u64p]),
+    "witch_measure_fp32_peak": (ctypes.c_double, [ctypes.c_double]),
     "witch_debug_fwdbwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, c_i32p, c_i32p, ctypes.c_int, c_f32p, c_f32p]),
 }
 

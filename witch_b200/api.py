@@ -56,6 +56,21 @@ class Queries:
         self._h = h
         self.n = len(seqs)
 
+    @classmethod
+    def from_buffer(cls, ehmm, residues_ptr, offsets):
+        """Queries from a caller-owned host buffer of concatenated ASCII residues (e.g. pinned memory): residues_ptr
+        is the integer address, offsets the int64 [n+1] starts."""
+        self = cls.__new__(cls)
+        self.ehmm = ehmm
+        self.offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        self.lengths = np.diff(self.offsets)
+        self.n = len(self.lengths)
+        h = ctypes.c_void_p()
+        check(_lib.load().witch_queries_create(ehmm._h, self.n, ctypes.cast(residues_ptr, ctypes.c_char_p),
+                                               _ptr(self.offsets, ctypes.c_int64), ctypes.byref(h)))
+        self._h = h
+        return self
+
     def close(self):
         if getattr(self, "_h", None):
             _lib.load().witch_queries_destroy(self._h)

@@ -290,3 +290,36 @@ extern "C" int witch_debug_fwdbwd(witch_ehmm *e, witch_queries *q, int n_pairs, 
         return fail(WITCH_ERR_CUDA, ex.what());
     }
 }
+
+extern "C" double witch_measure_fp32_peak(double ms_target) {
+    try {
+        require_device();
+        int dev = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+        DevBuf<float> out; out.alloc(4);
+        const int grid = prop.multiProcessorCount * 8, block = 256;
+        cudaEvent_t a, b;
+        CUDA_TRY(cudaEventCreate(&a)); CUDA_TRY(cudaEventCreate(&b));
+        int iters = 1 << 14;
+        double best = 0;
+        for (int rep = 0; rep < 6; rep++) {
+            CUDA_TRY(cudaEventRecord(a));
+            ffma_peak_kernel<<<grid, block>>>(out.p, iters);
+            g_launches++;
+            CUDA_TRY(cudaEventRecord(b));
+            CUDA_TRY(cudaEventSynchronize(b));
+            float ms = 0;
+            CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
+            const double tf = 2.0 * 8.0 * (double)iters * grid * block / (ms * 1e-3) / 1e12;
+            if (rep > 0) best = std::max(best, tf);
+            if (ms < ms_target && iters < (1 << 24)) iters *= 2;
+        }
+        cudaEventDestroy(a); cudaEventDestroy(b);
+        return best;
+    } catch (const std::exception &ex) {
+        g_err = ex.what();
+        return -1.0;
+    }
+}

@@ -104,4 +104,20 @@ __global__ void weights_topk_kernel(const float *scores, const uint8_t *reported
     if (lane == 0) count[q] = keep;
 }
 
+// FFMA micro-benchmark: 8 independent chains per thread.
+__global__ void ffma_peak_kernel(float *out, int iters) {
+    float a[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) a[j] = (float)(threadIdx.x + j) * 1e-3f;
+    const float b = 0.9999f, c = 1e-4f;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) a[j] = fmaf(a[j], b, c);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; j++) s += a[j];
+    if (s == 123.456f) out[0] = s;
+}
+
 }  // namespace witch

@@ -1,0 +1,180 @@
+"""Host-side mirror of the reference's interface for the eHMM score + align path.
+
+The function names, argument meaning and return types follow witch_msa/gcmm of the reference (WITCH v1.0.10) so
+that its call sites (gcmm/gcmm.py:160-161, 219-222, 241-244) can switch with a few lines:
+
+    reference                                               here
+    SearchAlgorithm.search          (algorithm.py:273-336)  BatchedSearch.search      -> one batched device call
+    evalHMMSearchOutput             (algorithm.py:579-605)  (no text to parse; the 1-decimal rounding is applied
+                                                             where the reference parsed the text)
+    rankBitscores                   (loader.py:299-376)     BatchedSearch.rankBitscores
+    calculateWeights/writeWeights   (weighting.py:58-169)   BatchedSearch.writeWeights
+    getBackbones(use_gcm=False)     (aligner.py:33-148)     BatchedSearch.getBackbones (all queries at once)
+    writeWeightsToLocal             (weighting.py:174-178)  writeWeightsToLocal
+
+All arithmetic runs in libwitch_b200.so on the GPU; this module only shapes inputs/outputs. torch is used to hold
+the score / weight tensors on the device between the stages (plumbing). No CPU fallback.
+"""
+import math
+
+import numpy as np
+
+from . import api
+
+
+def adaptive_inclusion_counts(w, count, target=0.999):
+    """Vectorised form of gcmm/aligner.py:58-63: per query, number of leading weights to keep so that their sum
+    reaches `target` (at least one when count > 0). Sequential float64 accumulation like the reference."""
+    n, k = w.shape
+    keep = np.zeros(n, dtype=np.int32)
+    cur = np.zeros(n, dtype=np.float64)
+    active = count > 0
+    for j in range(k):
+        take = active & (j < count) & (cur < target)
+        cur = np.where(take, cur + w[:, j], cur)
+        keep += take.astype(np.int32)
+    return keep
+
+
+class BatchedSearch:
+    """All-against-all query-HMM scoring, weighting and alignment on one GPU.
+
+    index_to_hmm order == order of `hmm_paths`; taxon names are the (already renamed) query names of the reference's
+    loadSubQueries (gcmm/loader.py:381-405)."""
+
+    def __init__(self, hmm_paths, num_hmms=10, use_weight=True):
+        self.ehmm = api.EHMM(hmm_paths)
+        self.num_hmms = int(num_hmms)
+        self.use_weight = use_weight
+        self.queries = None
+        self.taxa = None
+        self._dev = {}
+
+    # ------------------------------------------------------------------ score
+    def search(self, taxa, seqs):
+        """SearchAlgorithm.search: returns nothing in the reference (results go to files); here the device score
+        table is kept on `self` and also returned as numpy: (scores[n,H], reported[n,H])."""
+        self.taxa = list(taxa)
+        self.queries = api.Queries(self.ehmm, seqs)
+        scores, rep, pre, flags = api.score(self.ehmm, self.queries)
+        self.scores, self.reported, self.pre, self.flags = scores, rep, pre, flags
+        return scores, rep
+
+    def hmmsearch_results(self, h, evalue=0.0):
+        """The dict the reference writes per (HMM, chunk) file (algorithm.py:535-537): {taxon: (evalue, score)} with
+        the 1-decimal printed score. E-values are not used downstream (loader.py:293) and are reported as `evalue`."""
+        out = {}
+        for q, t in enumerate(self.taxa):
+            if self.reported[q, h]:
+                out[t] = (evalue, float("%.1f" % self.scores[q, h]))
+        return out
+
+    def rankBitscores(self):
+        """-> ranked_bitscores: {taxon: [(hmm_idx, score), ...]} sorted by score descending (loader.py:318-330)."""
+        ranked = {}
+        for q, t in enumerate(self.taxa):
+            idx = np.nonzero(self.reported[q])[0]
+            sc = [float("%.1f" % self.scores[q, h]) for h in idx]
+            ranked[t] = sorted(zip((int(h) for h in idx), sc), key=lambda x: x[1], reverse=True)
+        return ranked
+
+    def writeWeights(self):
+        """-> taxon_to_weights: {taxon: ((hmm_idx, weight), ...)} top num_hmms by weight (weighting.py:121-169).
+        Queries without any reported HMM are absent, as in the reference."""
+        idx, w, cnt = api.weights_topk(self.ehmm, self.scores, self.reported, self.num_hmms, 1)
+        self.top_idx, self.top_w, self.top_count = idx, w, cnt
+        out = {}
+        for q, t in enumerate(self.taxa):
+            if cnt[q] > 0:
+                out[t] = tuple((int(idx[q, j]), float(w[q, j])) for j in range(cnt[q]))
+        return out
+
+    # ------------------------------------------------------------------ align
+    def getBackbones(self, taxon_to_weights=None):
+        """Batched getBackbones(use_gcm=False) for every query: -> {taxon: (log_str, weights_map,
+        subset_to_aligned_columns)} exactly as aligner.py:33-148 returns per query."""
+        if taxon_to_weights is None:
+            taxon_to_weights = self.writeWeights()
+        name_to_q = {t: q for q, t in enumerate(self.taxa)}
+        pq, ph, owner = [], [], []
+        included = {}
+        for t, sw in taxon_to_weights.items():
+            if len(sw) == 0:
+                continue
+            if self.use_weight:
+                cur, i = 0.0, 0
+                while i < len(sw) and cur < 0.999:
+                    cur += sw[i][1]
+                    i += 1
+                top = [(x[0], float(x[1])) for x in sw[:i]]
+            else:
+                top = [(x[0], 1) for x in sw]
+            included[t] = top
+            for h, _ in top:
+                pq.append(name_to_q[t]); ph.append(h); owner.append(t)
+        cols = api.align(self.ehmm, self.queries, pq, ph)
+        out = {}
+        for t, sw in taxon_to_weights.items():
+            if len(sw) == 0:
+                out[t] = ("N/A", None)
+                continue
+            top = included[t]
+            log = "{}\tpassed to main pipeline with top {} weights: {}".format(t, len(top), top)
+            out[t] = (log, {i: w for (i, w) in sw}, {})
+        for t, h, c in zip(owner, ph, cols):
+            out[t][2][h] = [int(x) for x in c]
+        return out
+
+
+def writeWeightsToLocal(taxon_to_weights, path):
+    """weighting.py:174-178; plain floats (not numpy reprs) so that readWeightsFromLocal's eval works everywhere."""
+    with open(path, "w") as f:
+        for taxon, weights in taxon_to_weights.items():
+            f.write("{}:{}\n".format(taxon, tuple((int(i), float(w)) for i, w in weights)))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class DevicePipeline:
+    """The whole hot path with every intermediate kept in HBM (torch tensors): score -> weights/top-k -> adaptive
+    inclusion -> align. Used by bench.py and by the multi-GPU driver (witch_b200/sharding.py)."""
+
+    def __init__(self, ehmm, k=10, device=None):
+        import torch
+        self.torch = torch
+        self.ehmm = ehmm
+        self.k = k
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+
+    def run(self, queries, stream=None):
+        torch = self.torch
+        n, H, k = queries.n, self.ehmm.n, self.k
+        st = (stream or torch.cuda.current_stream(self.device)).cuda_stream
+        dev = self.device
+        scores = torch.empty((n, H), dtype=torch.float32, device=dev)
+        rep = torch.empty((n, H), dtype=torch.uint8, device=dev)
+        api.score_dev(self.ehmm, queries, scores.data_ptr(), rep.data_ptr(), 0, 0, st)
+        idx = torch.empty((n, k), dtype=torch.int32, device=dev)
+        w = torch.empty((n, k), dtype=torch.float64, device=dev)
+        cnt = torch.empty((n,), dtype=torch.int32, device=dev)
+        api.weights_topk_dev(self.ehmm, scores.data_ptr(), rep.data_ptr(), n, k, 1, idx.data_ptr(), w.data_ptr(),
+                             cnt.data_ptr(), st)
+        # adaptive inclusion needs the (tiny) top-k table on the host to size the align batch
+        idx_h, w_h, cnt_h = idx.cpu().numpy(), w.cpu().numpy(), cnt.cpu().numpy()
+        keep = adaptive_inclusion_counts(w_h, cnt_h)
+        qsel = np.repeat(np.arange(n, dtype=np.int32), keep)
+        jsel = np.concatenate([np.arange(c, dtype=np.int32) for c in keep]) if n else np.zeros(0, np.int32)
+        hsel = idx_h[qsel, jsel].astype(np.int32) if len(qsel) else np.zeros(0, np.int32)
+        lens = queries.lengths[qsel] if len(qsel) else np.zeros(0, np.int64)
+        off = np.zeros(len(qsel) + 1, dtype=np.int64)
+        np.cumsum(lens, out=off[1:])
+        cols = torch.full((max(int(off[-1]), 1),), -1, dtype=torch.int32, device=dev)
+        if len(qsel):
+            import ctypes
+            from . import _lib
+            _lib.check(_lib.load().witch_align_dev(
+                self.ehmm._h, queries._h, len(qsel), qsel.ctypes.data_as(_lib.c_i32p), hsel.ctypes.data_as(_lib.c_i32p),
+                off.ctypes.data_as(_lib.c_i64p), ctypes.c_void_p(cols.data_ptr()), ctypes.c_void_p(st)))
+        cells_score = float(queries.lengths.sum()) * float(self.ehmm.M.sum())
+        cells_align = float((lens * self.ehmm.M[hsel]).sum()) if len(qsel) else 0.0
+        return dict(scores=scores, reported=rep, idx=idx, w=w, count=cnt, pair_q=qsel, pair_h=hsel, col_off=off,
+                    cols=cols, keep=keep, cells_score=cells_score, cells_align=cells_align)
