@@ -120,6 +120,9 @@ def align(ehmm, queries, qidx, hidx):
     """Optimal-accuracy column lists for the given (query, HMM) pairs. -> list of int32 arrays."""
     qidx = np.ascontiguousarray(qidx, dtype=np.int32)
     hidx = np.ascontiguousarray(hidx, dtype=np.int32)
+    if len(qidx) != len(hidx) or (len(qidx) and (qidx.min() < 0 or qidx.max() >= queries.n
+                                                 or hidx.min() < 0 or hidx.max() >= ehmm.n)):
+        raise WitchError("witch_align: pair index out of range")
     lens = queries.lengths[qidx]
     off = np.zeros(len(qidx) + 1, dtype=np.int64)
     np.cumsum(lens, out=off[1:])

@@ -5,6 +5,13 @@
 
 namespace witch {
 
+// ln(1 + omega * exp(x)) without overflow for large x
+__device__ __forceinline__ float log1p_omega_exp(float x) {
+    const float lw = -5.545177444479562f;  // ln(1/256)
+    const float y = x + lw;
+    return y > 20.f ? y : log1pf(expf(y));
+}
+
 // One thread per (query, HMM) pair.
 __global__ void finalize_scores_kernel(const PairParse *parse, const int *qlen, int nq, int H,
                                        const int *env_base,      // [nq*H] first envelope slot of the pair
@@ -25,7 +32,6 @@ __global__ void finalize_scores_kernel(const PairParse *parse, const int *qlen, 
         const float fwd = pp.fwd_bits * LN2;
         prev = (fwd - nullsc) / LN2;
         if (pp.nenv > 0) {
-            const float omega = 1.0f / 256.0f;
             float sb = 0.f, S = 0.f, corr = 0.f;
             int Ld = 0;
             const int b = env_base[p];
@@ -34,9 +40,9 @@ __global__ void finalize_scores_kernel(const PairParse *parse, const int *qlen, 
                 sb += dc;
                 if (es - dc > 0.f) { S += es; Ld += pp.env_j[e] - pp.env_i[e] + 1; corr += dc; }
             }
-            const float seqbias = log1pf(omega * expf(sb));
+            const float seqbias = log1p_omega_exp(sb);
             float seq = (fwd - (nullsc + seqbias)) / LN2;
-            const float b2 = log1pf(omega * expf(corr));
+            const float b2 = log1p_omega_exp(corr);
             float sum = S + (L - (float)Ld) * logf(L / (L + 3.0f));
             sum = (sum - (nullsc + b2)) / LN2;
             if (Ld > 0 && sum > seq) { seq = sum; fl |= 2; }

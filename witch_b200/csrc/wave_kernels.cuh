@@ -271,6 +271,9 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQue
             const float *emis_right = emis_s + rs * SW + emis_index<C>(32, rl, 0);
             float *tM = tileM + (size_t)s * TT * SW, *tI = tileI + (size_t)s * TT * SW;
             if (firstS) { xNv = 0.f; xNg = g; }
+#ifdef WITCH_DEBUG_WAVE
+            bool dbg_bad = false;
+#endif
             for (int tp = 0; tp < nstepsB; tp++) {
                 const int i = Ls - (tp - (31 - lane));
                 const bool act = (i >= 0 && i <= Ls);
@@ -350,6 +353,13 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQue
                         }
 #pragma unroll
                         for (int c = 0; c < C; c++) { sM[c] = nM[c]; sI[c] = nI[c]; sD[c] = nD[c]; }
+#ifdef WITCH_DEBUG_WAVE
+                        if (!dbg_bad && (!isfinite(nM[0]) || !isfinite(nD[0]) || !isfinite(nI[0]) || !isfinite(nM[C-1]))) {
+                            dbg_bad = true;
+                            printf("BWD nonfinite pair %d strip %d lane %d tp %d row %d g %d nM0 %g nD0 %g nI0 %g cMb %g cDb %g ebs %g rMb %g mnR %g bndG %d\n",
+                                   it.pair, s, lane, tp, i, g, nM[0], nD[0], nI[0], cMb, cDb, ebs, rMb, mnR, (lane == 31 && !lastS) ? bndG[i] : -1);
+                        }
+#endif
                     }
                     rMb = cMb;
                     ebs *= ploop;
@@ -359,6 +369,9 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQue
                             // N_b(i) = N_b(i+1)*loop + B_b(i)*move   (N_b(Ls) = 0)
                             const float f = pow2i(xNg - g);
                             xNv = (i == Ls) ? 0.f : xNv * f * ploop + bp * pmove;
+#ifdef WITCH_DEBUG_WAVE
+                            if (!dbg_bad && !isfinite(xNv)) { dbg_bad = true; printf("XN nonfinite pair %d row %d tp %d g %d xNg %d f %g bp %g cB %g sM0 %g\n", it.pair, i, tp, g, xNg, f, bp, cB, sM[0]); }
+#endif
                             xNg = g;
                             rNB[i] = xNv; rNBg[i] = g;
                         }
@@ -368,6 +381,9 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQue
                     float mx = 0.f;
 #pragma unroll
                     for (int c = 0; c < C; c++) mx = fmaxf(mx, fmaxf(sM[c], fmaxf(sI[c], sD[c])));
+                    // the running B(i) partial carries the mass of every strip to the right, which can be far above
+                    // this strip's own cells: it must drive the exponent too (cells that flush are negligible)
+                    mx = fmaxf(mx, bp);
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
                     int e_need = (mx > 1048576.f) ? fexp(mx) : 0;

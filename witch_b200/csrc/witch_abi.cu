@@ -257,7 +257,7 @@ static std::vector<SClass> s_classes(const witch_ehmm *e, const std::vector<int>
 }
 
 template <int C>
-static void launch_parser(const witch_ehmm *e, const witch_queries *q, int T, ParserWork wk, cudaStream_t st) {
+static void launch_parser(const witch_ehmm *e, const witch_queries *q, int T, ParserWork wk, cudaStream_t st, int maxgrid) {
     const size_t smem = ((size_t)q->nsym * T * C + 9 * S_RED) * sizeof(float);
     if (smem > 200 * 1024) throw std::runtime_error("emission table does not fit shared memory (too many symbols x model length)");
     CUDA_TRY(cudaFuncSetAttribute(mh_parser_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -265,7 +265,7 @@ static void launch_parser(const witch_ehmm *e, const witch_queries *q, int T, Pa
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mh_parser_kernel<C>, T, smem));
     if (occ < 1) throw std::runtime_error("parser kernel cannot be resident (registers/shared memory)");
     const long long nitems = (long long)wk.nh * wk.nq;
-    const int grid = (int)std::min<long long>(nitems, (long long)e->num_sms * occ);
+    const int grid = (int)std::min<long long>(std::min<long long>(nitems, (long long)e->num_sms * occ), maxgrid);
     mh_parser_kernel<C><<<grid, T, smem, st>>>(e->view(), q->view(), wk);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
@@ -309,9 +309,9 @@ static void run_parser(witch_ehmm *e, witch_queries *q, const std::vector<int> &
         wk.Lcap = Lcap; wk.scratch = e->scratch.p; wk.counter = e->counter.p + ci; wk.out = e->parse.p;
         wk.dbg_bwd = d_dbg_bwd;
         switch (classes[ci].C) {
-            case 4: launch_parser<4>(e, q, classes[ci].T, wk, st); break;
-            case 8: launch_parser<8>(e, q, classes[ci].T, wk, st); break;
-            case 12: launch_parser<12>(e, q, classes[ci].T, wk, st); break;
+            case 4: launch_parser<4>(e, q, classes[ci].T, wk, st, maxgrid); break;
+            case 8: launch_parser<8>(e, q, classes[ci].T, wk, st, maxgrid); break;
+            case 12: launch_parser<12>(e, q, classes[ci].T, wk, st, maxgrid); break;
             default: throw std::runtime_error("bad class");
         }
     }
