@@ -44,7 +44,8 @@ static void run_wave(witch_ehmm *e, witch_queries *q, std::vector<WaveItem> item
             i = j;
         }
         const WaveLayout lay = wave_layout(Lcap, max_strips, C, ALIGN);
-        const size_t smem = (size_t)q->nsym * max_strips * SW * sizeof(float);
+        const int emis_floats = q->nsym * max_strips * SW;
+        const size_t smem = (size_t)emis_floats * sizeof(float) + (size_t)WAVE_WARPS * W_RES_CAP;
         if (smem > 200 * 1024) throw std::runtime_error("emission table does not fit shared memory");
         auto kern = wave_kernel<C, ALIGN>;
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -63,7 +64,7 @@ static void run_wave(witch_ehmm *e, witch_queries *q, std::vector<WaveItem> item
         WaveWork wk;
         wk.items = ditems.p; wk.group_first = dgf.p; wk.group_count = dgc.p; wk.ngroups = (int)gfirst.size();
         wk.counter = e->counter.p; wk.scratch = (char *)e->bytes.p; wk.slot_bytes = lay.total; wk.Lcap = Lcap;
-        wk.max_strips = max_strips; wk.envsc = d_envsc; wk.domcorr = d_domcorr; wk.cols = d_cols; wk.col_off = d_coloff;
+        wk.max_strips = max_strips; wk.emis_floats = emis_floats; wk.envsc = d_envsc; wk.domcorr = d_domcorr; wk.cols = d_cols; wk.col_off = d_coloff;
         wk.dbg_fwd = d_dbg_fwd; wk.dbg_bwd = d_dbg_bwd;
         {
             ScopedTimer tm(ALIGN ? 2 : 1, st, cells);

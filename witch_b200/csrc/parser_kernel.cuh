@@ -60,9 +60,10 @@ __device__ __forceinline__ void load_emis(const float *row, int T, int j, float 
 }
 
 constexpr int S_RED = 32;  // max warps per CTA
+constexpr int PARSER_SCRATCH_ROWS = 21;  // floats of scratch per sequence row and CTA
 
-template <int C>
-__global__ void __launch_bounds__(C == 4 ? 512 : (C == 8 ? 384 : 320)) mh_parser_kernel(DevEhmm E, DevQueries Q, ParserWork Wk) {
+template <int C, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) mh_parser_kernel(DevEhmm E, DevQueries Q, ParserWork Wk) {
     extern __shared__ float smem[];
     const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5, NW = T >> 5;
     const int TC = T * C;
@@ -75,13 +76,15 @@ __global__ void __launch_bounds__(C == 4 ? 512 : (C == 8 ? 384 : 320)) mh_parser
     float *s_bD = s_bI + 2 * S_RED;
     __shared__ int s_item;
 
-    const int stride_scr = 11 * (Wk.Lcap + 1);
-    float *Fs = Wk.scratch + (size_t)blockIdx.x * stride_scr;  // [(L+1)][6]: N,B,E,J,C,exp
-    float *dPB = Fs + 6 * (Wk.Lcap + 1);                       // P(B at i)
-    float *dPE = dPB + (Wk.Lcap + 1);                          // P(E at i)
-    float *dMO = dPE + (Wk.Lcap + 1);                          // mocc[i]
-    float *dBT = dMO + (Wk.Lcap + 1);                          // btot prefix
-    float *dET = dBT + (Wk.Lcap + 1);                          // etot prefix
+    const int Lr = (Wk.Lcap + 4) & ~3;                         // rows, rounded so that every array stays 16-byte aligned
+    const int stride_scr = PARSER_SCRATCH_ROWS * Lr;
+    float *Fs = Wk.scratch + (size_t)blockIdx.x * stride_scr;  // [(L+1)][8]: Forward N,B,E,J,C,exp
+    float *Bs = Fs + 8 * Lr;                                   // [(L+1)][8]: Backward B,E,N,J,C,exp
+    float *dPB = Bs + 8 * Lr;                                  // P(B at i)
+    float *dPE = dPB + Lr;                                     // P(E at i)
+    float *dMO = dPE + Lr;                                     // mocc[i]
+    float *dBT = dMO + Lr;                                     // btot prefix
+    float *dET = dBT + Lr;                                     // etot prefix
 
     const long long nitems = (long long)Wk.nh * Wk.nq;
     int loaded_h = -1;
@@ -94,7 +97,7 @@ __global__ void __launch_bounds__(C == 4 ? 512 : (C == 8 ? 384 : 320)) mh_parser
         const int h = Wk.hmms[item % Wk.nh];
         const int q = Wk.qorder[item / Wk.nh];
         const int L = Q.len[q];
-        const long long qoff = Q.off[q];
+        const uint8_t *__restrict__ qd = Q.dsq + Q.off[q];
         const long long po = E.poff[h];
         PairParse *res = Wk.out + (size_t)q * E.H + h;
         if (L <= 0) {
@@ -145,19 +148,27 @@ __global__ void __launch_bounds__(C == 4 ? 512 : (C == 8 ? 384 : 320)) mh_parser
             if (lane == 0) Cexcl = 1.f;
             if (lane == 31) s_pw[w] = Pc;
         }
+        __syncthreads();
+        // lane l of warp w keeps cz = prod_{l < w'' < w} PW[w'']  (0 for l >= w): Z_w = sum_l tot[l] * cz
+        float czl = 0.f;
+        if (lane < w) {
+            czl = 1.f;
+            for (int ww = lane + 1; ww < w; ww++) czl *= s_pw[ww];
+        }
         float sM[C], sI[C], sD[C];
 #pragma unroll
         for (int c = 0; c < C; c++) { sM[c] = 0.f; sI[c] = 0.f; sD[c] = 0.f; }
         float xN = 1.f, xB = pmove, xE = 0.f, xJ = 0.f, xC = 0.f;
         int sF = 0;
         if (tid == 0) { Fs[0] = xN; Fs[1] = xB; Fs[2] = 0.f; Fs[3] = 0.f; Fs[4] = 0.f; Fs[5] = 0.f; }
-        __syncthreads();  // emis_s, s_pw ready
-        int xres = Q.dsq[qoff];
+        __syncthreads();  // emis_s ready
+        int xres = qd[0];
         for (int i = 1; i <= L; i++) {
             float scl = 1.f;
             if (i > 1) {  // post(i-1)
-                float Et = 0.f;
-                for (int ww = 0; ww < NW; ww++) Et += s_es[ww];
+                float Et = (lane < NW) ? s_es[lane] : 0.f;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) Et += __shfl_xor_sync(0xffffffffu, Et, o);
                 xE = Et; xJ = xJ * ploop + Et * EJ; xC = xC * ploop + Et * EC; xN *= ploop; xB = (xN + xJ) * pmove;
                 if (Et > 1.0e12f) {
                     int e = fexp(Et);
@@ -167,14 +178,14 @@ __global__ void __launch_bounds__(C == 4 ? 512 : (C == 8 ? 384 : 320)) mh_parser
                     for (int c = 0; c < C; c++) { sM[c] *= scl; sI[c] *= scl; sD[c] *= scl; }
                 }
                 if (tid == 0) {
-                    float *r = Fs + 6 * (i - 1);
-                    r[0] = xN; r[1] = xB; r[2] = xE; r[3] = xJ; r[4] = xC; r[5] = (float)sF;
+                    float4 *r = reinterpret_cast<float4 *>(Fs + 8 * (i - 1));
+                    r[0] = make_float4(xN, xB, xE, xJ); r[1] = make_float4(xC, (float)sF, 0.f, 0.f);
                 }
             }
             // pre(i)
             float e[C];
             load_emis<C>(emis_s + (size_t)xres * TC, T, tid, e);
-            if (i < L) xres = Q.dsq[qoff + i];
+            if (i < L) xres = qd[i];
             float mL = __shfl_up_sync(0xffffffffu, sM[C - 1], 1);
             float iL = __shfl_up_sync(0xffffffffu, sI[C - 1], 1);
             float dL = __shfl_up_sync(0xffffffffu, sD[C - 1], 1);
@@ -212,8 +223,9 @@ __global__ void __launch_bounds__(C == 4 ? 512 : (C == 8 ? 384 : 320)) mh_parser
             }
             __syncthreads();
             // mid(i)
-            float Z = 0.f;
-            for (int ww = 0; ww < w; ww++) Z = fmaf(s_pw[ww], Z, s_tot[ww]);
+            float Z = (lane < NW) ? s_tot[lane] * czl : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) Z += __shfl_xor_sync(0xffffffffu, Z, o);
             const float X = fmaf(Cexcl, Z, yex);
             float es = 0.f;
 #pragma unroll
@@ -229,12 +241,13 @@ __global__ void __launch_bounds__(C == 4 ? 512 : (C == 8 ? 384 : 320)) mh_parser
             __syncthreads();
         }
         {  // post(L)
-            float Et = 0.f;
-            for (int ww = 0; ww < NW; ww++) Et += s_es[ww];
+            float Et = (lane < NW) ? s_es[lane] : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) Et += __shfl_xor_sync(0xffffffffu, Et, o);
             xE = Et; xJ = xJ * ploop + Et * EJ; xC = xC * ploop + Et * EC; xN *= ploop; xB = (xN + xJ) * pmove;
             if (tid == 0) {
-                float *r = Fs + 6 * L;
-                r[0] = xN; r[1] = xB; r[2] = xE; r[3] = xJ; r[4] = xC; r[5] = (float)sF;
+                float4 *r = reinterpret_cast<float4 *>(Fs + 8 * L);
+                r[0] = make_float4(xN, xB, xE, xJ); r[1] = make_float4(xC, (float)sF, 0.f, 0.f);
             }
         }
         const float Tm = xC * pmove;  // total = Tm * 2^sF
@@ -265,6 +278,12 @@ __global__ void __launch_bounds__(C == 4 ? 512 : (C == 8 ? 384 : 320)) mh_parser
             if (lane == 31) Cexcl = 1.f;
             if (lane == 0) s_pw[w] = Pc;
         }
+        __syncthreads();
+        czl = 0.f;  // Z_w = sum_{l > w} tot[l] * prod_{w < w'' < l} PW[w'']
+        if (lane > w && lane < NW) {
+            czl = 1.f;
+            for (int ww = w + 1; ww < lane; ww++) czl *= s_pw[ww];
+        }
 #pragma unroll
         for (int c = 0; c < C; c++) { sM[c] = 0.f; sI[c] = 0.f; sD[c] = 0.f; }
         float bN = 0.f, bJ = 0.f, bC = 0.f, bE = 0.f;
@@ -275,7 +294,7 @@ __global__ void __launch_bounds__(C == 4 ? 512 : (C == 8 ? 384 : 320)) mh_parser
             float mn[C], mnR[C];
             float eR = 0.f;
             if (i < L) {
-                const int xr = Q.dsq[qoff + i];
+                const int xr = qd[i];
                 float e[C];
                 const float *erow = emis_s + (size_t)xr * TC;
                 load_emis<C>(erow, T, tid, e);
@@ -304,16 +323,11 @@ __global__ void __launch_bounds__(C == 4 ? 512 : (C == 8 ? 384 : 320)) mh_parser
                 nI[c] = fmaf(mnR[c], pb[c], sI[c] * pii[c]);
                 tm[c] = mnR[c] * pg[c];
             }
-            // Forward specials needed by the decoding of row i (thread 0 only)
-            float f0[6], f1[6];
-            if (tid == 0) {
-#pragma unroll
-                for (int z = 0; z < 6; z++) { f1[z] = Fs[6 * i + z]; f0[z] = (i > 0) ? Fs[6 * (i - 1) + z] : 0.f; }
-            }
             __syncthreads();
             // mid(i)
-            float Bi = 0.f;
-            for (int ww = 0; ww < NW; ww++) Bi += s_es[ww];
+            float Bi = (lane < NW) ? s_es[lane] : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) Bi += __shfl_xor_sync(0xffffffffu, Bi, o);
             if (i == L) { bC = pmove; bJ = 0.f; bN = 0.f; }
             else { bJ = bJ * ploop + Bi * pmove; bC = bC * ploop; bN = bN * ploop + Bi * pmove; }
             bE = bJ * EJ + bC * EC;
@@ -328,15 +342,9 @@ __global__ void __launch_bounds__(C == 4 ? 512 : (C == 8 ? 384 : 320)) mh_parser
                     for (int c = 0; c < C; c++) { Mp[c] *= scl; nI[c] *= scl; tm[c] *= scl; }
                 }
             }
-            if (tid == 0) {
-                // P(B at i), P(E at i), mocc[i]  
-                const float fii = exp2f(f1[5] + (float)(sB - sT)) * invT;
-                dPB[i] = f1[1] * Bi * fii;
-                dPE[i] = f1[2] * bE * fii;
-                if (i > 0) {
-                    const float fpi = exp2f(f0[5] + (float)(sB - sT)) * invT * ploop;
-                    dMO[i] = 1.0f - (f0[0] * bN + f0[3] * bJ + f0[4] * bC) * fpi;
-                } else dMO[0] = 0.f;
+            if (tid == 0) {  // backward specials of row i, decoded after the sweep
+                float4 *r = reinterpret_cast<float4 *>(Bs + 8 * i);
+                r[0] = make_float4(Bi, bE, bN, bJ); r[1] = make_float4(bC, (float)sB, 0.f, 0.f);
             }
             if (i == 0) break;
             float dl[C];
@@ -354,8 +362,9 @@ __global__ void __launch_bounds__(C == 4 ? 512 : (C == 8 ? 384 : 320)) mh_parser
             if (lane == 0) s_tot[w] = y;
             __syncthreads();
             // post(i)
-            float Z = 0.f;
-            for (int ww = NW - 1; ww > w; ww--) Z = fmaf(s_pw[ww], Z, s_tot[ww]);
+            float Z = (lane < NW) ? s_tot[lane] * czl : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) Z += __shfl_xor_sync(0xffffffffu, Z, o);
             const float X = fmaf(Cexcl, Z, yex);  // D(i, first column of the right neighbour)
 #pragma unroll
             for (int c = C - 1; c >= 0; c--) {
@@ -370,6 +379,22 @@ __global__ void __launch_bounds__(C == 4 ? 512 : (C == 8 ? 384 : 320)) mh_parser
         if (Wk.dbg_bwd != nullptr && tid == 0)
             Wk.dbg_bwd[(size_t)q * E.H + h] = (logf(bN) + (float)sB * 0.69314718056f);
 
+        // ---- posterior decoding of the special states, parallel over rows ----
+        __syncthreads();
+        for (int i = tid; i <= L; i += T) {
+            const float4 f1a = reinterpret_cast<const float4 *>(Fs + 8 * i)[0], f1b = reinterpret_cast<const float4 *>(Fs + 8 * i)[1];
+            const float4 b1a = reinterpret_cast<const float4 *>(Bs + 8 * i)[0], b1b = reinterpret_cast<const float4 *>(Bs + 8 * i)[1];
+            const float fii = exp2f(f1b.y + b1b.y - (float)sT) * invT;
+            dPB[i] = f1a.y * b1a.x * fii;   // F_B(i) * B_B(i) / T
+            dPE[i] = f1a.z * b1a.y * fii;   // F_E(i) * B_E(i) / T
+            float mo = 0.f;
+            if (i > 0) {
+                const float4 f0a = reinterpret_cast<const float4 *>(Fs + 8 * (i - 1))[0], f0b = reinterpret_cast<const float4 *>(Fs + 8 * (i - 1))[1];
+                const float fpi = exp2f(f0b.y + b1b.y - (float)sT) * invT * ploop;
+                mo = 1.0f - (f0a.x * b1a.z + f0a.w * b1a.w + f0b.x * b1b.x) * fpi;   // N, J, C
+            }
+            dMO[i] = mo;
+        }
         // =========================== regions (warp 0) ===========================
         __syncthreads();
         if (w == 0) {

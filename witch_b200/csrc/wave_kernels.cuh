@@ -33,6 +33,7 @@ struct WaveWork {
     long long slot_bytes;
     int Lcap;       // max Ls in this launch
     int max_strips;
+    int emis_floats;  // floats reserved for the emission table in dynamic shared memory (residue staging follows)
     // outputs (envelope mode)
     float *envsc;   // [nitems] ln P(envelope | unihit model)
     float *domcorr; // [nitems] sum of ln null2 over the envelope
@@ -44,6 +45,7 @@ struct WaveWork {
 
 constexpr int WAVE_WARPS = 4;  // warps per CTA (they share one HMM's emission table in shared memory)
 constexpr int W_SCALE_EVERY = 8;
+constexpr int W_RES_CAP = 4096;  // residues of one item staged in shared memory per warp (longer items read HBM)
 
 // scratch layout helper (all offsets in bytes, per warp slot)
 struct WaveLayout {
@@ -126,6 +128,12 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQue
         const WaveItem it = Wk.items[gfirst + w];
         const int Ls = it.Ls, Lfull = Q.len[it.q];
         const uint8_t *dsq = Q.dsq + Q.off[it.q] + (it.i0 - 1);  // dsq[i-1] = residue i of the envelope
+        if (it.Ls <= W_RES_CAP) {  // stage the item's residues in shared memory (one byte each)
+            uint8_t *sr = reinterpret_cast<uint8_t *>(emis_s + Wk.emis_floats) + w * W_RES_CAP;
+            for (int z = lane; z < it.Ls; z += 32) sr[z] = dsq[z];
+            __syncwarp();
+            dsq = sr;
+        }
         const long long po = E.poff[h];
         const float pmove = 2.0f / ((float)Lfull + 2.0f), ploop = 1.0f - pmove;
         const unsigned FULL = 0xffffffffu;
@@ -153,6 +161,10 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQue
             const float *emis_strip = emis_s + s * SW;
             float *tM = tileM + (size_t)s * TT * SW, *tI = tileI + (size_t)s * TT * SW;
             if (last) { xCv = 0.f; xCg = g; }
+            int xcur = dsq[min(max(-lane, 0), Ls - 1)];  // residue of the lane's row at the next step
+            float pbM = 0.f, pbI = 0.f, pbD = 0.f, pbE = 0.f;  // strip boundary of lane 0's next row (prefetched)
+            int pbG = 0;
+            if (s > 0) { pbM = bndM[1]; pbI = bndI[1]; pbD = bndD[1]; pbE = bndE[1]; pbG = bndG[1]; }
             for (int t = 1; t <= nsteps; t++) {
                 const int i = t - lane;
                 const bool act = (i >= 1 && i <= Ls);
@@ -163,13 +175,19 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQue
                 float cE = __shfl_up_sync(FULL, ep, 1);
                 if (lane == 0) {
                     if (s > 0 && act) {
-                        const float f = pow2i(bndG[i] - g);
-                        cM = bndM[i] * f; cI = bndI[i] * f; cD = bndD[i] * f; cE = bndE[i] * f;
+                        const float f = pow2i(pbG - g);
+                        cM = pbM * f; cI = pbI * f; cD = pbD * f; cE = pbE * f;
                     } else { cM = 0.f; cI = 0.f; cD = 0.f; cE = 0.f; }
                 }
+                if (s > 0) {  // prefetch the boundary of row t+1 (uniform address, consumed by lane 0 next step)
+                    const int ib = min(t + 1, Ls);
+                    pbM = bndM[ib]; pbI = bndI[ib]; pbD = bndD[ib]; pbE = bndE[ib]; pbG = bndG[ib];
+                }
+                const int xres = xcur;
+                xcur = dsq[min(max(i, 0), Ls - 1)];
                 if (act) {
                     float e[C];
-                    load_emis<C>(emis_strip + (size_t)dsq[i - 1] * Mstr, 32, lane, e);
+                    load_emis<C>(emis_strip + (size_t)xres * Mstr, 32, lane, e);
                     float nM[C], nI[C], nD[C];
 #pragma unroll
                     for (int c = C - 1; c >= 0; c--) {
@@ -274,6 +292,18 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQue
 #ifdef WITCH_DEBUG_WAVE
             bool dbg_bad = false;
 #endif
+            int xcur = dsq[min(max(Ls - 1 + (31 - lane), 0), Ls - 1)];  // residue i+1 of the lane's row at the next step
+            float pbM = 0.f, pbD = 0.f, pbE = 0.f;
+            int pbG = 0, gFn = 0;
+            if (!lastS) { pbM = bndM[Ls]; pbD = bndD[Ls]; pbE = bndE[Ls]; pbG = bndG[Ls]; }
+            float FMn[C], FIn[C];  // forward row of the next step (prefetched)
+            {
+                const int tF0 = Ls + 31;
+                gFn = gFarr[s * TT + tF0];
+                const float *fm = tM + ((size_t)tF0 * 32 + lane) * C, *fi = tI + ((size_t)tF0 * 32 + lane) * C;
+#pragma unroll
+                for (int c = 0; c < C; c++) { FMn[c] = fm[c]; FIn[c] = fi[c]; }
+            }
             for (int tp = 0; tp < nstepsB; tp++) {
                 const int i = Ls - (tp - (31 - lane));
                 const bool act = (i >= 0 && i <= Ls);
@@ -282,15 +312,41 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQue
                 float cB = __shfl_down_sync(FULL, bp, 1);
                 if (lane == 31) {
                     if (!lastS && act) {
-                        const float f = pow2i(bndG[i] - g);
-                        cMb = bndM[i] * f; cDb = bndD[i] * f; cB = bndE[i] * f;
+                        const float f = pow2i(pbG - g);
+                        cMb = pbM * f; cDb = pbD * f; cB = pbE * f;
                     } else { cMb = 0.f; cDb = 0.f; cB = 0.f; }
                 }
+                if (!lastS) {  // prefetch the boundary of lane 31's next row (uniform address)
+                    const int ib = max(Ls - tp - 1, 0);
+                    pbM = bndM[ib]; pbD = bndD[ib]; pbE = bndE[ib]; pbG = bndG[ib];
+                }
                 const int tF = Ls + 31 - tp;  // forward tile row holding row i of this lane (valid for i >= 1)
+                float FMv[C], FIv[C];
+                const int gFc = gFn;
+#pragma unroll
+                for (int c = 0; c < C; c++) { FMv[c] = FMn[c]; FIv[c] = FIn[c]; }
+                {   // prefetch the forward row and exponent of the next step
+                    const int tFn = max(tF - 1, 0);
+                    gFn = gFarr[s * TT + tFn];
+                    const float *fmn = tM + ((size_t)tFn * 32 + lane) * C, *fin = tI + ((size_t)tFn * 32 + lane) * C;
+                    if (C % 4 == 0) {
+#pragma unroll
+                        for (int v = 0; v < C / 4; v++) {
+                            float4 a = reinterpret_cast<const float4 *>(fmn)[v], b = reinterpret_cast<const float4 *>(fin)[v];
+                            FMn[4 * v] = a.x; FMn[4 * v + 1] = a.y; FMn[4 * v + 2] = a.z; FMn[4 * v + 3] = a.w;
+                            FIn[4 * v] = b.x; FIn[4 * v + 1] = b.y; FIn[4 * v + 2] = b.z; FIn[4 * v + 3] = b.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < C; c++) { FMn[c] = fmn[c]; FIn[c] = fin[c]; }
+                    }
+                }
+                const int xres = xcur;
+                xcur = dsq[min(max(i - 1, 0), Ls - 1)];
                 if (act) {
                     float mn[C], mnR;
                     if (i < Ls) {
-                        const int xr = dsq[i];
+                        const int xr = xres;
                         float e[C];
                         load_emis<C>(emis_strip + (size_t)xr * Mstr, 32, lane, e);
 #pragma unroll
@@ -316,20 +372,8 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQue
                             nI[c] = fmaf(m1, oIM[c], sI[c] * oII[c]);
                         }
                         // posterior decoding against the stored forward row
-                        const float fac = exp2f((float)(gFarr[s * TT + tF] + g - gT)) * invT;
+                        const float fac = exp2f((float)(gFc + g - gT)) * invT;
                         float *fm = tM + ((size_t)tF * 32 + lane) * C, *fi = tI + ((size_t)tF * 32 + lane) * C;
-                        float FMv[C], FIv[C];
-                        if (C % 4 == 0) {
-#pragma unroll
-                            for (int v = 0; v < C / 4; v++) {
-                                float4 a = reinterpret_cast<const float4 *>(fm)[v], b = reinterpret_cast<const float4 *>(fi)[v];
-                                FMv[4 * v] = a.x; FMv[4 * v + 1] = a.y; FMv[4 * v + 2] = a.z; FMv[4 * v + 3] = a.w;
-                                FIv[4 * v] = b.x; FIv[4 * v + 1] = b.y; FIv[4 * v + 2] = b.z; FIv[4 * v + 3] = b.w;
-                            }
-                        } else {
-#pragma unroll
-                            for (int c = 0; c < C; c++) { FMv[c] = fm[c]; FIv[c] = fi[c]; }
-                        }
                         if (ALIGN) {
                             float pM[C], pI[C];
 #pragma unroll

@@ -256,17 +256,17 @@ static std::vector<SClass> s_classes(const witch_ehmm *e, const std::vector<int>
     return out;
 }
 
-template <int C>
+template <int C, int MAXT, int MINB>
 static void launch_parser(const witch_ehmm *e, const witch_queries *q, int T, ParserWork wk, cudaStream_t st, int maxgrid) {
     const size_t smem = ((size_t)q->nsym * T * C + 9 * S_RED) * sizeof(float);
     if (smem > 200 * 1024) throw std::runtime_error("emission table does not fit shared memory (too many symbols x model length)");
-    CUDA_TRY(cudaFuncSetAttribute(mh_parser_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(mh_parser_kernel<C, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mh_parser_kernel<C>, T, smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mh_parser_kernel<C, MAXT, MINB>, T, smem));
     if (occ < 1) throw std::runtime_error("parser kernel cannot be resident (registers/shared memory)");
     const long long nitems = (long long)wk.nh * wk.nq;
     const int grid = (int)std::min<long long>(std::min<long long>(nitems, (long long)e->num_sms * occ), maxgrid);
-    mh_parser_kernel<C><<<grid, T, smem, st>>>(e->view(), q->view(), wk);
+    mh_parser_kernel<C, MAXT, MINB><<<grid, T, smem, st>>>(e->view(), q->view(), wk);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
 }
@@ -281,7 +281,7 @@ static void run_parser(witch_ehmm *e, witch_queries *q, const std::vector<int> &
     e->i1.upload(qorder, st);
     const int Lcap = q->maxlen + 1;
     int maxgrid = e->num_sms * 8;
-    e->scratch.alloc((size_t)maxgrid * 11 * (Lcap + 1));
+    e->scratch.alloc((size_t)maxgrid * PARSER_SCRATCH_ROWS * (size_t)((Lcap + 4) & ~3) + 64);
     e->counter.alloc(64);
     auto classes = s_classes(e, hsel);
     std::vector<int> allh;
@@ -308,10 +308,11 @@ static void run_parser(witch_ehmm *e, witch_queries *q, const std::vector<int> &
         wk.qorder = e->i1.p; wk.nq = (int)qorder.size();
         wk.Lcap = Lcap; wk.scratch = e->scratch.p; wk.counter = e->counter.p + ci; wk.out = e->parse.p;
         wk.dbg_bwd = d_dbg_bwd;
+        const int T = classes[ci].T;
         switch (classes[ci].C) {
-            case 4: launch_parser<4>(e, q, classes[ci].T, wk, st, maxgrid); break;
-            case 8: launch_parser<8>(e, q, classes[ci].T, wk, st, maxgrid); break;
-            case 12: launch_parser<12>(e, q, classes[ci].T, wk, st, maxgrid); break;
+            case 4: if (T <= 256) launch_parser<4, 256, 2>(e, q, T, wk, st, maxgrid); else launch_parser<4, 512, 1>(e, q, T, wk, st, maxgrid); break;
+            case 8: if (T <= 256) launch_parser<8, 256, 2>(e, q, T, wk, st, maxgrid); else launch_parser<8, 384, 1>(e, q, T, wk, st, maxgrid); break;
+            case 12: launch_parser<12, 320, 1>(e, q, T, wk, st, maxgrid); break;
             default: throw std::runtime_error("bad class");
         }
     }
