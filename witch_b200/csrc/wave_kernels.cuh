@@ -58,7 +58,7 @@ __host__ __device__ inline WaveLayout wave_layout(int Lcap, int max_strips, int 
     long long tile = (long long)max_strips * w.TT * 32 * C * 4;
     long long o = 0;
     w.tileM = o; o += tile;
-    w.tileI = o; o += tile;
+    w.tileI = o; if (align) o += tile;  // insert rows are kept for the align stage only
     w.gF = o; o += (long long)max_strips * w.TT * 4;
     w.bnd = o; o += (long long)6 * (Lcap + 2) * 4;    // bndM,bndI,bndD,bndE,bndG,(spare)
     w.rows = o; o += (long long)10 * (Lcap + 2) * 4;  // FC,FCg,NB,NBg,NOA,PPC,EOA,KE,...
@@ -208,15 +208,17 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQue
                     xBs *= ploop;
                     // keep the row for posterior decoding (wave layout)
                     float *dm = tM + ((size_t)t * 32 + lane) * C, *di = tI + ((size_t)t * 32 + lane) * C;
+                    // (envelope mode needs match posteriors only: sum over emitting states of a row's posteriors is 1,
+                    //  so fI + fNCJ = 1 - sum_k fM(k); insert rows are stored for the align stage only)
                     if (C % 4 == 0) {
 #pragma unroll
                         for (int v = 0; v < C / 4; v++) {
                             reinterpret_cast<float4 *>(dm)[v] = make_float4(nM[4 * v], nM[4 * v + 1], nM[4 * v + 2], nM[4 * v + 3]);
-                            reinterpret_cast<float4 *>(di)[v] = make_float4(nI[4 * v], nI[4 * v + 1], nI[4 * v + 2], nI[4 * v + 3]);
+                            if (ALIGN) reinterpret_cast<float4 *>(di)[v] = make_float4(nI[4 * v], nI[4 * v + 1], nI[4 * v + 2], nI[4 * v + 3]);
                         }
                     } else {
 #pragma unroll
-                        for (int c = 0; c < C; c++) { dm[c] = nM[c]; di[c] = nI[c]; }
+                        for (int c = 0; c < C; c++) { dm[c] = nM[c]; if (ALIGN) di[c] = nI[c]; }
                     }
                     if (lane == 31) {
                         if (!last) { bndM[i] = sM[C - 1]; bndI[i] = sI[C - 1]; bndD[i] = sD[C - 1]; bndE[i] = ep; bndG[i] = g; }
@@ -263,7 +265,7 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQue
         // ======================================= Backward =======================================
         // lane l processes row i = Ls - (t' - (31 - l)), rows Ls .. 0 (row 0 only feeds the B special)
         float xNv = 0.f; int xNg = 0;  // N special (lane 0 of strip 0)
-        float accI = 0.f;             // expected insert uses (envelope mode)
+        float accI = 0.f;             // sum of all match posteriors (envelope mode)
         if (!ALIGN && lane < MAX_SYM) s_n2[w][lane] = 0.f;
         __syncwarp();
         const int nstepsB = Ls + 1 + 31;
@@ -302,7 +304,7 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQue
                 gFn = gFarr[s * TT + tF0];
                 const float *fm = tM + ((size_t)tF0 * 32 + lane) * C, *fi = tI + ((size_t)tF0 * 32 + lane) * C;
 #pragma unroll
-                for (int c = 0; c < C; c++) { FMn[c] = fm[c]; FIn[c] = fi[c]; }
+                for (int c = 0; c < C; c++) { FMn[c] = fm[c]; FIn[c] = ALIGN ? fi[c] : 0.f; }
             }
             for (int tp = 0; tp < nstepsB; tp++) {
                 const int i = Ls - (tp - (31 - lane));
@@ -332,13 +334,16 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQue
                     if (C % 4 == 0) {
 #pragma unroll
                         for (int v = 0; v < C / 4; v++) {
-                            float4 a = reinterpret_cast<const float4 *>(fmn)[v], b = reinterpret_cast<const float4 *>(fin)[v];
+                            float4 a = reinterpret_cast<const float4 *>(fmn)[v];
                             FMn[4 * v] = a.x; FMn[4 * v + 1] = a.y; FMn[4 * v + 2] = a.z; FMn[4 * v + 3] = a.w;
-                            FIn[4 * v] = b.x; FIn[4 * v + 1] = b.y; FIn[4 * v + 2] = b.z; FIn[4 * v + 3] = b.w;
+                            if (ALIGN) {
+                                float4 b = reinterpret_cast<const float4 *>(fin)[v];
+                                FIn[4 * v] = b.x; FIn[4 * v + 1] = b.y; FIn[4 * v + 2] = b.z; FIn[4 * v + 3] = b.w;
+                            }
                         }
                     } else {
 #pragma unroll
-                        for (int c = 0; c < C; c++) { FMn[c] = fmn[c]; FIn[c] = fin[c]; }
+                        for (int c = 0; c < C; c++) { FMn[c] = fmn[c]; if (ALIGN) FIn[c] = fin[c]; }
                     }
                 }
                 const int xres = xcur;
@@ -390,10 +395,7 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQue
                             }
                         } else {
 #pragma unroll
-                            for (int c = 0; c < C; c++) {
-                                accM[c] = fmaf(FMv[c] * nM[c], fac, accM[c]);
-                                accI = fmaf(FIv[c] * nI[c], fac, accI);
-                            }
+                            for (int c = 0; c < C; c++) accM[c] = fmaf(FMv[c] * nM[c], fac, accM[c]);
                         }
 #pragma unroll
                         for (int c = 0; c < C; c++) { sM[c] = nM[c]; sI[c] = nI[c]; sD[c] = nD[c]; }
@@ -457,6 +459,12 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQue
                     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
                     if (lane == 0) s_n2[w][x] += v;
                 }
+                float v = 0.f;
+#pragma unroll
+                for (int c = 0; c < C; c++) v += accM[c];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+                accI += v;  // running sum_k sum_i ppM(i,k)  (warp-uniform)
             }
             if (firstS) { xNv = __shfl_sync(FULL, xNv, 0); xNg = __shfl_sync(FULL, xNg, 0); }
             __syncwarp();
@@ -465,8 +473,7 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQue
 
         // N / C flank posteriors: ppN(i) = F_N(i-1) B_N(i) loop / T ; ppC(i) = F_C(i-1) B_C(i) loop / T
         // F_N(i) = loop^i, B_C(i) = move * loop^(Ls-i)
-        float fX = 0.f;
-        {
+        if (ALIGN) {
             const float l2loop = log2f(ploop), l2move = log2f(pmove), l2T = log2f(Tm) + (float)gT;
             for (int base = 1; base <= Ls; base += 32) {
                 const int i = base + lane;
@@ -479,28 +486,23 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQue
                         const float fc = rFC[i - 1];
                         pc = (fc > 0.f) ? exp2f(log2f(fc) + (float)rFCg[i - 1] + l2move + (float)(Ls - i + 1) * l2loop - l2T) : 0.f;
                     }
-                    if (ALIGN) { rNOA[i] = pn; rPPC[i] = pc; }
+                    rNOA[i] = pn; rPPC[i] = pc;
                 }
-                fX += pn + pc;
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) fX += __shfl_xor_sync(FULL, fX, o);
         }
 
         if (!ALIGN) {
             // ---- null2 by expectation ----
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) accI += __shfl_xor_sync(FULL, accI, o);
             __syncwarp();
             const int K = (E.Kp == 29) ? 20 : 4;
             const float norm = 1.0f / (float)Ls;
             // log null2 per dense symbol, computed by lanes x < nsym
             float ln2 = 0.f;
             if (lane < Q.nsym) {
-                if (lane < K) ln2 = logf((s_n2[w][lane] + accI + fX) * norm);
+                if (lane < K) ln2 = logf((s_n2[w][lane] - accI) * norm + 1.0f);
             }
             __syncwarp();
-            if (lane < K) s_n2[w][lane] = (s_n2[w][lane] + accI + fX) * norm;
+            if (lane < K) s_n2[w][lane] = (s_n2[w][lane] - accI) * norm + 1.0f;
             __syncwarp();
             if (lane >= K && lane < Q.nsym) {
                 // degenerate symbol: unweighted mean of the canonical null2 odds over its members
