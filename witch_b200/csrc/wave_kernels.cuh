@@ -59,12 +59,34 @@ __host__ __device__ inline WaveLayout wave_layout(int Lcap, int max_strips, int 
     long long o = 0;
     w.tileM = o; o += tile;
     w.tileI = o; if (align) o += tile;  // insert rows are kept for the align stage only
-    w.gF = o; o += (long long)max_strips * w.TT * 4;
-    w.bnd = o; o += (long long)6 * (Lcap + 2) * 4;    // bndM,bndI,bndD,bndE,bndG,(spare)
+    w.gF = o; o += ((long long)max_strips * (w.TT / 8 + 2) * 4 + 15) / 16 * 16;  // one exponent per 8 steps
+    w.bnd = o; o += (long long)8 * (Lcap + 2) * 4;    // boundary records {M,I,D,E,G,-,-,-} per row
     w.rows = o; o += (long long)10 * (Lcap + 2) * 4;  // FC,FCg,NB,NBg,NOA,PPC,EOA,KE,...
     w.bits = o; if (align) o += (long long)max_strips * w.TT * 32 * 4;
     w.total = (o + 255) / 256 * 256;
     return w;
+}
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float4 lds_f4(unsigned a) {
+    float4 v;
+    asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float lds_f1(unsigned a) { float v; asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ int lds_u8(unsigned a) { unsigned v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return (int)v; }
+// Opaque identity: stops ptxas/nvcc from rebuilding a cheap-looking address expression inside the step loop
+#define PIN32(x) asm volatile("" : "+r"(x))
+#define PIN64(x) asm volatile("" : "+l"(x))
+// emission odds of C consecutive columns for symbol row at shared address `a` (strip-interleaved layout)
+template <int C>
+__device__ __forceinline__ void lds_emis(unsigned a, float (&e)[C]) {
+    static_assert(C % 4 == 0, "wave kernels need C % 4 == 0");
+#pragma unroll
+    for (int v = 0; v < C / 4; v++) {
+        const float4 t = lds_f4(a + v * 512);
+        e[4 * v] = t.x; e[4 * v + 1] = t.y; e[4 * v + 2] = t.z; e[4 * v + 3] = t.w;
+    }
 }
 
 // comparator for select_e (HMMER visits cells in striped order; M uses >=, D uses >): returns true if
@@ -77,19 +99,28 @@ __device__ __forceinline__ bool oa_e_better(float v2, int d2, int o2, float v1, 
 }
 
 template <int C, bool ALIGN>
-__global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQueries Q, WaveWork Wk) {
+__global__ void __launch_bounds__(WAVE_WARPS * 32, ALIGN ? 2 : 3) wave_kernel(DevEhmm E, DevQueries Q, WaveWork Wk) {
     extern __shared__ float smem[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     __shared__ int s_group;
     __shared__ float s_n2[WAVE_WARPS][MAX_SYM];
     float *emis_s = smem;  // [nsym][Mstr] in strip-interleaved layout
     const WaveLayout lay = wave_layout(Wk.Lcap, Wk.max_strips, C, ALIGN);
-    char *slot = Wk.scratch + ((long long)blockIdx.x * WAVE_WARPS + w) * Wk.slot_bytes;
+    __shared__ char *s_slot[WAVE_WARPS];
+    if (lane == 0) s_slot[w] = Wk.scratch + ((long long)blockIdx.x * WAVE_WARPS + w) * Wk.slot_bytes;
+    __syncwarp();
+    char *slot = *((char *volatile *)&s_slot[w]);  // a loaded value: keeps the compiler from rebuilding it from blockIdx
+    __builtin_assume(__isGlobal(slot));
     float *tileM = (float *)(slot + lay.tileM), *tileI = (float *)(slot + lay.tileI);
     int *gFarr = (int *)(slot + lay.gF);
     const int LB = Wk.Lcap + 2;
-    float *bndM = (float *)(slot + lay.bnd), *bndI = bndM + LB, *bndD = bndI + LB, *bndE = bndD + LB;
-    int *bndG = (int *)(bndE + LB);
+    float *bnd = (float *)(slot + lay.bnd);  // records of 8 words per row
+    int *bndi = (int *)bnd;
+#define BND_M(i) bnd[8 * (i)]
+#define BND_I(i) bnd[8 * (i) + 1]
+#define BND_D(i) bnd[8 * (i) + 2]
+#define BND_E(i) bnd[8 * (i) + 3]
+#define BND_G(i) bndi[8 * (i) + 4]
     float *rFC = (float *)(slot + lay.rows);
     int *rFCg = (int *)(rFC + LB);
     float *rNB = (float *)(rFCg + LB);
@@ -97,7 +128,8 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQue
     float *rNOA = (float *)(rNBg + LB), *rPPC = rNOA + LB, *rEOA = rPPC + LB;
     int *rKE = (int *)(rEOA + LB);
     unsigned *bits = (unsigned *)(slot + lay.bits);
-    const int TT = lay.TT;
+    const int TT = lay.TT, TG = lay.TT / 8 + 2;
+    const unsigned emis_sa = smem_u32(emis_s);
     const int SW = 32 * C;  // strip width
 
     int loaded_h = -1, Mstr = 0;
@@ -128,12 +160,14 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQue
         const WaveItem it = Wk.items[gfirst + w];
         const int Ls = it.Ls, Lfull = Q.len[it.q];
         const uint8_t *dsq = Q.dsq + Q.off[it.q] + (it.i0 - 1);  // dsq[i-1] = residue i of the envelope
-        if (it.Ls <= W_RES_CAP) {  // stage the item's residues in shared memory (one byte each)
+        const bool staged = it.Ls <= W_RES_CAP;
+        const unsigned sres = emis_sa + Wk.emis_floats * 4 + w * W_RES_CAP;
+        if (staged) {  // stage the item's residues in shared memory (one byte each)
             uint8_t *sr = reinterpret_cast<uint8_t *>(emis_s + Wk.emis_floats) + w * W_RES_CAP;
             for (int z = lane; z < it.Ls; z += 32) sr[z] = dsq[z];
             __syncwarp();
-            dsq = sr;
         }
+#define RES_AT(idx) (staged ? lds_u8(sresp + (idx)) : (int)dsq[(idx)])
         const long long po = E.poff[h];
         const float pmove = 2.0f / ((float)Lfull + 2.0f), ploop = 1.0f - pmove;
         const unsigned FULL = 0xffffffffu;
@@ -155,16 +189,22 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQue
             for (int c = 0; c < C; c++) { sM[c] = 0.f; sI[c] = 0.f; sD[c] = 0.f; }
             float rM = 0.f, rI = 0.f, rD = 0.f;      // row i-1 at the column left of the owned block
             float ep = 0.f;                          // running E(i) partial of the lane's last row
-            int g = (s > 0) ? bndG[1] : 0;           // warp exponent
+            int g = (s > 0) ? BND_G(1) : 0;           // warp exponent
             float xBs = pmove * pow2i(-g);           // pmove * N(i-1) * 2^-g for the lane's next row
             const bool last = (s == nstrips - 1);
-            const float *emis_strip = emis_s + s * SW;
+            unsigned ebase = emis_sa + (s * SW + lane * 4) * 4;
+            unsigned erow = Mstr * 4;
             float *tM = tileM + (size_t)s * TT * SW, *tI = tileI + (size_t)s * TT * SW;
+            int toff = (32 + lane) * C;  // element offset of (step t, lane) in the strip's wave-layout tile
+            int *gFs = gFarr + s * TG;
+            unsigned sresp = sres;
+            PIN32(ebase); PIN32(erow); PIN64(tM); PIN64(gFs); PIN32(sresp);
+            if (ALIGN) PIN64(tI);
             if (last) { xCv = 0.f; xCg = g; }
-            int xcur = dsq[min(max(-lane, 0), Ls - 1)];  // residue of the lane's row at the next step
+            int xcur = RES_AT(min(max(-lane, 0), Ls - 1));  // residue of the lane's row at the next step
             float pbM = 0.f, pbI = 0.f, pbD = 0.f, pbE = 0.f;  // strip boundary of lane 0's next row (prefetched)
             int pbG = 0;
-            if (s > 0) { pbM = bndM[1]; pbI = bndI[1]; pbD = bndD[1]; pbE = bndE[1]; pbG = bndG[1]; }
+            if (s > 0) { pbM = BND_M(1); pbI = BND_I(1); pbD = BND_D(1); pbE = BND_E(1); pbG = BND_G(1); }
             for (int t = 1; t <= nsteps; t++) {
                 const int i = t - lane;
                 const bool act = (i >= 1 && i <= Ls);
@@ -181,13 +221,13 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQue
                 }
                 if (s > 0) {  // prefetch the boundary of row t+1 (uniform address, consumed by lane 0 next step)
                     const int ib = min(t + 1, Ls);
-                    pbM = bndM[ib]; pbI = bndI[ib]; pbD = bndD[ib]; pbE = bndE[ib]; pbG = bndG[ib];
+                    pbM = BND_M(ib); pbI = BND_I(ib); pbD = BND_D(ib); pbE = BND_E(ib); pbG = BND_G(ib);
                 }
                 const int xres = xcur;
-                xcur = dsq[min(max(i, 0), Ls - 1)];
+                xcur = RES_AT(min(max(i, 0), Ls - 1));
                 if (act) {
                     float e[C];
-                    load_emis<C>(emis_strip + (size_t)xres * Mstr, 32, lane, e);
+                    lds_emis<C>(ebase + xres * erow, e);
                     float nM[C], nI[C], nD[C];
 #pragma unroll
                     for (int c = C - 1; c >= 0; c--) {
@@ -207,7 +247,7 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQue
                     rM = cM; rI = cI; rD = cD;
                     xBs *= ploop;
                     // keep the row for posterior decoding (wave layout)
-                    float *dm = tM + ((size_t)t * 32 + lane) * C, *di = tI + ((size_t)t * 32 + lane) * C;
+                    float *dm = tM + toff, *di = tI + toff;
                     // (envelope mode needs match posteriors only: sum over emitting states of a row's posteriors is 1,
                     //  so fI + fNCJ = 1 - sum_k fM(k); insert rows are stored for the align stage only)
                     if (C % 4 == 0) {
@@ -221,7 +261,7 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQue
                         for (int c = 0; c < C; c++) { dm[c] = nM[c]; if (ALIGN) di[c] = nI[c]; }
                     }
                     if (lane == 31) {
-                        if (!last) { bndM[i] = sM[C - 1]; bndI[i] = sI[C - 1]; bndD[i] = sD[C - 1]; bndE[i] = ep; bndG[i] = g; }
+                        if (!last) { BND_M(i) = sM[C - 1]; BND_I(i) = sI[C - 1]; BND_D(i) = sD[C - 1]; BND_E(i) = ep; BND_G(i) = g; }
                         else {
                             // C(i) = C(i-1)*loop + E(i)   (unihit: E->C = 1), with exponent alignment
                             const float f = pow2i(xCg - g);
@@ -230,7 +270,8 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQue
                         }
                     }
                 }
-                if (lane == 0) gFarr[s * TT + t] = g;
+                toff += 32 * C;
+                if (((t - 1) & 7) == 0 && lane == 0) gFs[(t - 1) >> 3] = g;  // exponent of steps t .. t+7
                 if ((t & (W_SCALE_EVERY - 1)) == 0) {
                     float mx = 0.f;
 #pragma unroll
@@ -240,7 +281,7 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQue
                     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
                     int e_need = (mx > 1048576.f) ? fexp(mx) : 0;
                     if (s > 0) {
-                        int ahead = bndG[min(Ls, t + W_SCALE_EVERY)] - 40 - g;
+                        int ahead = BND_G(min(Ls, t + W_SCALE_EVERY)) - 40 - g;
                         e_need = max(e_need, ahead);
                     }
                     if (e_need > 0) {
@@ -282,27 +323,30 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQue
             float rMb = 0.f;   // Mb(i+1, first column right of my block)
             float bp = 0.f;    // running B(i) partial
             const bool lastS = (s == nstrips - 1), firstS = (s == 0);
-            int g = lastS ? 0 : bndG[Ls];
+            int g = lastS ? 0 : BND_G(Ls);
             float ebs = pmove * pow2i(-g);  // E(i) = C_b(i) = pmove * loop^(Ls-i), scaled
-            const float *emis_strip = emis_s + s * SW;
+            unsigned ebase = emis_sa + (s * SW + lane * 4) * 4;
+            unsigned erow = Mstr * 4;
             // emission of the first column of the right neighbour's block (k0 + C + 1)
             const int rs = (lane == 31) ? s + 1 : s, rl = (lane == 31) ? 0 : lane + 1;
             const bool hasR = !(lastS && lane == 31);
-            const float *emis_right = emis_s + rs * SW + emis_index<C>(32, rl, 0);
+            unsigned eright = emis_sa + (rs * SW + emis_index<C>(32, rl, 0)) * 4;
             float *tM = tileM + (size_t)s * TT * SW, *tI = tileI + (size_t)s * TT * SW;
+            const int *gFs = gFarr + s * TG;
+            unsigned sresp = sres;
+            PIN32(ebase); PIN32(erow); PIN32(eright); PIN64(tM); PIN64(gFs); PIN32(sresp);
+            if (ALIGN) PIN64(tI);
             if (firstS) { xNv = 0.f; xNg = g; }
-#ifdef WITCH_DEBUG_WAVE
-            bool dbg_bad = false;
-#endif
-            int xcur = dsq[min(max(Ls - 1 + (31 - lane), 0), Ls - 1)];  // residue i+1 of the lane's row at the next step
+            int xcur = RES_AT(Ls - 1);  // residue i+1 of the lane's row at the next step
             float pbM = 0.f, pbD = 0.f, pbE = 0.f;
-            int pbG = 0, gFn = 0;
-            if (!lastS) { pbM = bndM[Ls]; pbD = bndD[Ls]; pbE = bndE[Ls]; pbG = bndG[Ls]; }
+            int pbG = 0;
+            if (!lastS) { pbM = BND_M(Ls); pbD = BND_D(Ls); pbE = BND_E(Ls); pbG = BND_G(Ls); }
             float FMn[C], FIn[C];  // forward row of the next step (prefetched)
+            int toff = ((Ls + 31) * 32 + lane) * C;  // tile element offset of the forward row matching the current step
+            int gFc = gFs[(Ls + 30) >> 3];
+            float fac = exp2f((float)(gFc + g - gT)) * invT;  // posterior scale; refreshed when an exponent changes
             {
-                const int tF0 = Ls + 31;
-                gFn = gFarr[s * TT + tF0];
-                const float *fm = tM + ((size_t)tF0 * 32 + lane) * C, *fi = tI + ((size_t)tF0 * 32 + lane) * C;
+                const float *fm = tM + toff, *fi = tI + toff;
 #pragma unroll
                 for (int c = 0; c < C; c++) { FMn[c] = fm[c]; FIn[c] = ALIGN ? fi[c] : 0.f; }
             }
@@ -320,17 +364,16 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQue
                 }
                 if (!lastS) {  // prefetch the boundary of lane 31's next row (uniform address)
                     const int ib = max(Ls - tp - 1, 0);
-                    pbM = bndM[ib]; pbD = bndD[ib]; pbE = bndE[ib]; pbG = bndG[ib];
+                    pbM = BND_M(ib); pbD = BND_D(ib); pbE = BND_E(ib); pbG = BND_G(ib);
                 }
                 const int tF = Ls + 31 - tp;  // forward tile row holding row i of this lane (valid for i >= 1)
                 float FMv[C], FIv[C];
-                const int gFc = gFn;
 #pragma unroll
                 for (int c = 0; c < C; c++) { FMv[c] = FMn[c]; FIv[c] = FIn[c]; }
-                {   // prefetch the forward row and exponent of the next step
-                    const int tFn = max(tF - 1, 0);
-                    gFn = gFarr[s * TT + tFn];
-                    const float *fmn = tM + ((size_t)tFn * 32 + lane) * C, *fin = tI + ((size_t)tFn * 32 + lane) * C;
+                const int toffc = toff;
+                if (tp + 1 < nstepsB) {   // prefetch the forward row of the next step (tile row 0 exists and is never used)
+                    toff -= 32 * C;
+                    const float *fmn = tM + toff, *fin = tI + toff;
                     if (C % 4 == 0) {
 #pragma unroll
                         for (int v = 0; v < C / 4; v++) {
@@ -347,16 +390,16 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQue
                     }
                 }
                 const int xres = xcur;
-                xcur = dsq[min(max(i - 1, 0), Ls - 1)];
+                xcur = RES_AT(min(max(i - 1, 0), Ls - 1));
                 if (act) {
                     float mn[C], mnR;
                     if (i < Ls) {
                         const int xr = xres;
                         float e[C];
-                        load_emis<C>(emis_strip + (size_t)xr * Mstr, 32, lane, e);
+                        lds_emis<C>(ebase + xr * erow, e);
 #pragma unroll
                         for (int c = 0; c < C; c++) mn[c] = sM[c] * e[c];
-                        mnR = hasR ? rMb * emis_right[(size_t)xr * Mstr] : 0.f;
+                        mnR = hasR ? rMb * lds_f1(eright + xr * erow) : 0.f;
                     } else {
 #pragma unroll
                         for (int c = 0; c < C; c++) mn[c] = 0.f;
@@ -377,8 +420,7 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQue
                             nI[c] = fmaf(m1, oIM[c], sI[c] * oII[c]);
                         }
                         // posterior decoding against the stored forward row
-                        const float fac = exp2f((float)(gFc + g - gT)) * invT;
-                        float *fm = tM + ((size_t)tF * 32 + lane) * C, *fi = tI + ((size_t)tF * 32 + lane) * C;
+                        float *fm = tM + toffc, *fi = tI + toffc;
                         if (ALIGN) {
                             float pM[C], pI[C];
 #pragma unroll
@@ -399,29 +441,23 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQue
                         }
 #pragma unroll
                         for (int c = 0; c < C; c++) { sM[c] = nM[c]; sI[c] = nI[c]; sD[c] = nD[c]; }
-#ifdef WITCH_DEBUG_WAVE
-                        if (!dbg_bad && (!isfinite(nM[0]) || !isfinite(nD[0]) || !isfinite(nI[0]) || !isfinite(nM[C-1]))) {
-                            dbg_bad = true;
-                            printf("BWD nonfinite pair %d strip %d lane %d tp %d row %d g %d nM0 %g nD0 %g nI0 %g cMb %g cDb %g ebs %g rMb %g mnR %g bndG %d\n",
-                                   it.pair, s, lane, tp, i, g, nM[0], nD[0], nI[0], cMb, cDb, ebs, rMb, mnR, (lane == 31 && !lastS) ? bndG[i] : -1);
-                        }
-#endif
                     }
                     rMb = cMb;
                     ebs *= ploop;
                     if (lane == 0) {
-                        if (!firstS) { bndM[i] = sM[0]; bndD[i] = sD[0]; bndE[i] = bp; bndG[i] = g; }
+                        if (!firstS) { BND_M(i) = sM[0]; BND_D(i) = sD[0]; BND_E(i) = bp; BND_G(i) = g; }
                         else {
                             // N_b(i) = N_b(i+1)*loop + B_b(i)*move   (N_b(Ls) = 0)
                             const float f = pow2i(xNg - g);
                             xNv = (i == Ls) ? 0.f : xNv * f * ploop + bp * pmove;
-#ifdef WITCH_DEBUG_WAVE
-                            if (!dbg_bad && !isfinite(xNv)) { dbg_bad = true; printf("XN nonfinite pair %d row %d tp %d g %d xNg %d f %g bp %g cB %g sM0 %g\n", it.pair, i, tp, g, xNg, f, bp, cB, sM[0]); }
-#endif
                             xNg = g;
                             rNB[i] = xNv; rNBg[i] = g;
                         }
                     }
+                }
+                if (((tF - 1) & 7) == 0 && tF > 1) {  // next step enters the previous exponent block
+                    gFc = gFs[(tF - 2) >> 3];
+                    fac = exp2f((float)(gFc + g - gT)) * invT;
                 }
                 if ((tp & (W_SCALE_EVERY - 1)) == (W_SCALE_EVERY - 1)) {
                     float mx = 0.f;
@@ -434,7 +470,7 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQue
                     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
                     int e_need = (mx > 1048576.f) ? fexp(mx) : 0;
                     if (!lastS) {
-                        int ahead = bndG[max(0, Ls - (tp + W_SCALE_EVERY))] - 40 - g;
+                        int ahead = BND_G(max(0, Ls - (tp + W_SCALE_EVERY))) - 40 - g;
                         e_need = max(e_need, ahead);
                     }
                     if (e_need > 0) {
@@ -443,6 +479,7 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQue
 #pragma unroll
                         for (int c = 0; c < C; c++) { sM[c] *= f; sI[c] *= f; sD[c] *= f; }
                         rMb *= f; bp *= f; ebs *= f;
+                        fac = exp2f((float)(gFc + g - gT)) * invT;
                     }
                 }
             }
@@ -451,7 +488,7 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQue
                 const int K = (E.Kp == 29) ? 20 : 4;
                 for (int x = 0; x < K; x++) {
                     float e[C];
-                    load_emis<C>(emis_strip + (size_t)x * Mstr, 32, lane, e);
+                    lds_emis<C>(ebase + x * erow, e);
                     float v = 0.f;
 #pragma unroll
                     for (int c = 0; c < C; c++) v = fmaf(accM[c], e[c], v);
@@ -520,10 +557,11 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQue
                 ln2 = cnt ? logf(sum / (float)cnt) : 0.f;
             }
             // domain correction = sum over envelope residues of ln null2[x]
+            const unsigned sresp = sres;
             float dc = 0.f;
             for (int base = 0; base < Ls; base += 32) {
                 const int p = base + lane;
-                const int xr = (p < Ls) ? dsq[p] : 0;
+                const int xr = (p < Ls) ? RES_AT(p) : 0;
                 for (int z = 0; z < 32 && base + z < Ls; z++) {
                     const int xx = __shfl_sync(FULL, xr, z);
                     dc += __shfl_sync(FULL, ln2, xx);
@@ -578,7 +616,7 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQue
                     float cEV = __shfl_up_sync(FULL, eV, 1);
                     int cEK = __shfl_up_sync(FULL, eK, 1);
                     if (lane == 0) {
-                        if (!first && act) { cM = bndM[i]; cI = bndI[i]; cD = bndD[i]; cEV = bndE[i]; cEK = bndG[i]; }
+                        if (!first && act) { cM = BND_M(i); cI = BND_I(i); cD = BND_D(i); cEV = BND_E(i); cEK = BND_G(i); }
                         else { cM = NEG; cI = NEG; cD = NEG; cEV = NEG; cEK = 0; }
                     }
                     if (act) {
@@ -644,7 +682,7 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) wave_kernel(DevEhmm E, DevQue
                         for (int c = 0; c < C; c++) { oM[c] = nM[c]; oI[c] = nI[c]; oD[c] = nD[c]; }
                         rM = cM; rI = cI; rD = cD;
                         if (lane == 31) {
-                            if (!last) { bndM[i] = oM[C - 1]; bndI[i] = oI[C - 1]; bndD[i] = oD[C - 1]; bndE[i] = eV; bndG[i] = eK; }
+                            if (!last) { BND_M(i) = oM[C - 1]; BND_I(i) = oI[C - 1]; BND_D(i) = oD[C - 1]; BND_E(i) = eV; BND_G(i) = eK; }
                             else { rEOA[i] = eV; rKE[i] = eK; }
                         }
                     }
