@@ -60,12 +60,30 @@ __device__ __forceinline__ void load_emis(const float *row, int T, int j, float 
 }
 
 constexpr int S_RED = 32;  // max warps per CTA
+
+// 32-bit shared-memory addressing helpers: keep hot-loop addresses as one pinned register + immediate offsets
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float4 lds_f4(unsigned a) {
+    float4 v;
+    asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float lds_f1(unsigned a) { float v; asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float lds_f1v(unsigned a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts_f1(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ int lds_u8(unsigned a) { unsigned v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return (int)v; }
+// Opaque identity: stops the compiler from rebuilding a cheap-looking address expression inside the row loop
+#define PIN32(x) asm volatile("" : "+r"(x))
+#define PIN64(x) asm volatile("" : "+l"(x))
 constexpr int PARSER_SCRATCH_ROWS = 21;  // floats of scratch per sequence row and CTA
 
 template <int C, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) mh_parser_kernel(DevEhmm E, DevQueries Q, ParserWork Wk) {
     extern __shared__ float smem[];
-    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5, NW = T >> 5;
+    int T = blockDim.x, tid = threadIdx.x;
+    PIN32(T); PIN32(tid);
+    int lane = tid & 31, w = tid >> 5, NW = T >> 5;
+    PIN32(lane); PIN32(w); PIN32(NW);
     const int TC = T * C;
     float *emis_s = smem;                       // [nsym][TC]
     float *s_tot = emis_s + (size_t)Q.nsym * TC;  // [32]
@@ -73,7 +91,17 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser_kernel(DevEhmm E, DevQue
     float *s_pw = s_es + S_RED;
     float *s_bM = s_pw + S_RED;  // [2][32]
     float *s_bI = s_bM + 2 * S_RED;
-    float *s_bD = s_bI + 2 * S_RED;
+    (void)s_bI;
+    unsigned red_sa = smem_u32(s_tot);           // reduction area: tot, es, pw, bM[2], bI[2], bD[2] (32 words each)
+    unsigned emis_ta = smem_u32(emis_s) + tid * 16;  // this thread's slot in an emission row (interleaved layout)
+    unsigned erow_b = TC * 4, estep = T * 16;
+    PIN32(red_sa); PIN32(emis_ta); PIN32(erow_b); PIN32(estep);
+#define SA_TOT(x) (red_sa + 4 * (x))
+#define SA_ES(x) (red_sa + 128 + 4 * (x))
+#define SA_PW(x) (red_sa + 256 + 4 * (x))
+#define SA_BM(par, x) (red_sa + 384 + 128 * (par) + 4 * (x))
+#define SA_BI(par, x) (red_sa + 640 + 128 * (par) + 4 * (x))
+#define SA_BD(par, x) (red_sa + 896 + 128 * (par) + 4 * (x))
     __shared__ int s_item;
 
     const int Lr = (Wk.Lcap + 4) & ~3;                         // rows, rounded so that every array stays 16-byte aligned
@@ -146,14 +174,14 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser_kernel(DevEhmm E, DevQue
             }
             Cexcl = __shfl_up_sync(0xffffffffu, Pc, 1);
             if (lane == 0) Cexcl = 1.f;
-            if (lane == 31) s_pw[w] = Pc;
+            if (lane == 31) sts_f1(SA_PW(w), Pc);
         }
         __syncthreads();
         // lane l of warp w keeps cz = prod_{l < w'' < w} PW[w'']  (0 for l >= w): Z_w = sum_l tot[l] * cz
         float czl = 0.f;
         if (lane < w) {
             czl = 1.f;
-            for (int ww = lane + 1; ww < w; ww++) czl *= s_pw[ww];
+            for (int ww = lane + 1; ww < w; ww++) czl *= lds_f1v(SA_PW(ww));
         }
         float sM[C], sI[C], sD[C];
 #pragma unroll
@@ -163,10 +191,12 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser_kernel(DevEhmm E, DevQue
         if (tid == 0) { Fs[0] = xN; Fs[1] = xB; Fs[2] = 0.f; Fs[3] = 0.f; Fs[4] = 0.f; Fs[5] = 0.f; }
         __syncthreads();  // emis_s ready
         int xres = qd[0];
+        float4 *fsrow = reinterpret_cast<float4 *>(Fs + 8);  // row i-1 is written while row i is computed
+        PIN64(fsrow);
         for (int i = 1; i <= L; i++) {
             float scl = 1.f;
             if (i > 1) {  // post(i-1)
-                float Et = (lane < NW) ? s_es[lane] : 0.f;
+                float Et = (lane < NW) ? lds_f1v(SA_ES(lane)) : 0.f;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) Et += __shfl_xor_sync(0xffffffffu, Et, o);
                 xE = Et; xJ = xJ * ploop + Et * EJ; xC = xC * ploop + Et * EC; xN *= ploop; xB = (xN + xJ) * pmove;
@@ -178,21 +208,28 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser_kernel(DevEhmm E, DevQue
                     for (int c = 0; c < C; c++) { sM[c] *= scl; sI[c] *= scl; sD[c] *= scl; }
                 }
                 if (tid == 0) {
-                    float4 *r = reinterpret_cast<float4 *>(Fs + 8 * (i - 1));
-                    r[0] = make_float4(xN, xB, xE, xJ); r[1] = make_float4(xC, (float)sF, 0.f, 0.f);
+                    fsrow[0] = make_float4(xN, xB, xE, xJ); fsrow[1] = make_float4(xC, (float)sF, 0.f, 0.f);
                 }
+                fsrow += 2;
             }
             // pre(i)
             float e[C];
-            load_emis<C>(emis_s + (size_t)xres * TC, T, tid, e);
+            {
+                const unsigned ea = emis_ta + xres * erow_b;
+#pragma unroll
+                for (int v = 0; v < C / 4; v++) {
+                    const float4 t4 = lds_f4(ea + v * estep);
+                    e[4 * v] = t4.x; e[4 * v + 1] = t4.y; e[4 * v + 2] = t4.z; e[4 * v + 3] = t4.w;
+                }
+            }
             if (i < L) xres = qd[i];
             float mL = __shfl_up_sync(0xffffffffu, sM[C - 1], 1);
             float iL = __shfl_up_sync(0xffffffffu, sI[C - 1], 1);
             float dL = __shfl_up_sync(0xffffffffu, sD[C - 1], 1);
             if (lane == 0) {
                 if (w > 0 && i > 1) {
-                    const int bb = ((i - 1) & 1) * S_RED + w - 1;
-                    mL = s_bM[bb] * scl; iL = s_bI[bb] * scl; dL = s_bD[bb] * scl;
+                    const int par = (i - 1) & 1;
+                    mL = lds_f1v(SA_BM(par, w - 1)) * scl; iL = lds_f1v(SA_BI(par, w - 1)) * scl; dL = lds_f1v(SA_BD(par, w - 1)) * scl;
                 } else { mL = 0.f; iL = 0.f; dL = 0.f; }
             }
             float nM[C], nI[C];
@@ -217,13 +254,13 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser_kernel(DevEhmm E, DevQue
             float yex = __shfl_up_sync(0xffffffffu, y, 1);
             if (lane == 0) yex = 0.f;
             if (lane == 31) {
-                s_tot[w] = y;
-                s_bM[(i & 1) * S_RED + w] = nM[C - 1];
-                s_bI[(i & 1) * S_RED + w] = nI[C - 1];
+                sts_f1(SA_TOT(w), y);
+                sts_f1(SA_BM(i & 1, w), nM[C - 1]);
+                sts_f1(SA_BI(i & 1, w), nI[C - 1]);
             }
             __syncthreads();
             // mid(i)
-            float Z = (lane < NW) ? s_tot[lane] * czl : 0.f;
+            float Z = (lane < NW) ? lds_f1v(SA_TOT(lane)) * czl : 0.f;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) Z += __shfl_xor_sync(0xffffffffu, Z, o);
             const float X = fmaf(Cexcl, Z, yex);
@@ -236,12 +273,12 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser_kernel(DevEhmm E, DevQue
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) es += __shfl_xor_sync(0xffffffffu, es, o);
-            if (lane == 0) s_es[w] = es;
-            if (lane == 31) s_bD[(i & 1) * S_RED + w] = sD[C - 1];
+            if (lane == 0) sts_f1(SA_ES(w), es);
+            if (lane == 31) sts_f1(SA_BD(i & 1, w), sD[C - 1]);
             __syncthreads();
         }
         {  // post(L)
-            float Et = (lane < NW) ? s_es[lane] : 0.f;
+            float Et = (lane < NW) ? lds_f1v(SA_ES(lane)) : 0.f;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) Et += __shfl_xor_sync(0xffffffffu, Et, o);
             xE = Et; xJ = xJ * ploop + Et * EJ; xC = xC * ploop + Et * EC; xN *= ploop; xB = (xN + xJ) * pmove;
@@ -276,19 +313,21 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser_kernel(DevEhmm E, DevQue
             }
             Cexcl = __shfl_down_sync(0xffffffffu, Pc, 1);
             if (lane == 31) Cexcl = 1.f;
-            if (lane == 0) s_pw[w] = Pc;
+            if (lane == 0) sts_f1(SA_PW(w), Pc);
         }
         __syncthreads();
         czl = 0.f;  // Z_w = sum_{l > w} tot[l] * prod_{w < w'' < l} PW[w'']
         if (lane > w && lane < NW) {
             czl = 1.f;
-            for (int ww = w + 1; ww < lane; ww++) czl *= s_pw[ww];
+            for (int ww = w + 1; ww < lane; ww++) czl *= lds_f1v(SA_PW(ww));
         }
 #pragma unroll
         for (int c = 0; c < C; c++) { sM[c] = 0.f; sI[c] = 0.f; sD[c] = 0.f; }
         float bN = 0.f, bJ = 0.f, bC = 0.f, bE = 0.f;
         int sB = 0;
         const float invT = 1.0f / Tm;
+        float4 *bsrow = reinterpret_cast<float4 *>(Bs + 8 * L);
+        PIN64(bsrow);
         for (int i = L; i >= 0; i--) {
             // pre(i): consume row i+1 and residue i+1
             float mn[C], mnR[C];
@@ -296,9 +335,13 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser_kernel(DevEhmm E, DevQue
             if (i < L) {
                 const int xr = qd[i];
                 float e[C];
-                const float *erow = emis_s + (size_t)xr * TC;
-                load_emis<C>(erow, T, tid, e);
-                if (tid + 1 < T) eR = erow[emis_index<C>(T, tid + 1, 0)];
+                const unsigned ea = emis_ta + xr * erow_b;
+#pragma unroll
+                for (int v = 0; v < C / 4; v++) {
+                    const float4 t4 = lds_f4(ea + v * estep);
+                    e[4 * v] = t4.x; e[4 * v + 1] = t4.y; e[4 * v + 2] = t4.z; e[4 * v + 3] = t4.w;
+                }
+                if (tid + 1 < T) eR = lds_f1(ea + 16);  // first column of the right neighbour
 #pragma unroll
                 for (int c = 0; c < C; c++) mn[c] = sM[c] * e[c];
             } else {
@@ -306,7 +349,7 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser_kernel(DevEhmm E, DevQue
                 for (int c = 0; c < C; c++) mn[c] = 0.f;
             }
             float nb = __shfl_down_sync(0xffffffffu, mn[0], 1);
-            if (lane == 31) nb = (w + 1 < NW && i < L) ? s_bM[((i + 1) & 1) * S_RED + w + 1] * eR : 0.f;
+            if (lane == 31) nb = (w + 1 < NW && i < L) ? lds_f1v(SA_BM((i + 1) & 1, w + 1)) * eR : 0.f;
             float bp = 0.f;
 #pragma unroll
             for (int c = 0; c < C; c++) {
@@ -315,7 +358,7 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser_kernel(DevEhmm E, DevQue
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) bp += __shfl_xor_sync(0xffffffffu, bp, o);
-            if (lane == 0) s_es[w] = bp;
+            if (lane == 0) sts_f1(SA_ES(w), bp);
             float Mp[C], nI[C], tm[C];
 #pragma unroll
             for (int c = 0; c < C; c++) {
@@ -325,7 +368,7 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser_kernel(DevEhmm E, DevQue
             }
             __syncthreads();
             // mid(i)
-            float Bi = (lane < NW) ? s_es[lane] : 0.f;
+            float Bi = (lane < NW) ? lds_f1v(SA_ES(lane)) : 0.f;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) Bi += __shfl_xor_sync(0xffffffffu, Bi, o);
             if (i == L) { bC = pmove; bJ = 0.f; bN = 0.f; }
@@ -343,9 +386,9 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser_kernel(DevEhmm E, DevQue
                 }
             }
             if (tid == 0) {  // backward specials of row i, decoded after the sweep
-                float4 *r = reinterpret_cast<float4 *>(Bs + 8 * i);
-                r[0] = make_float4(Bi, bE, bN, bJ); r[1] = make_float4(bC, (float)sB, 0.f, 0.f);
+                bsrow[0] = make_float4(Bi, bE, bN, bJ); bsrow[1] = make_float4(bC, (float)sB, 0.f, 0.f);
             }
+            bsrow -= 2;
             if (i == 0) break;
             float dl[C];
             dl[C - 1] = tm[C - 1] + bE;
@@ -359,10 +402,10 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser_kernel(DevEhmm E, DevQue
             }
             float yex = __shfl_down_sync(0xffffffffu, y, 1);
             if (lane == 31) yex = 0.f;
-            if (lane == 0) s_tot[w] = y;
+            if (lane == 0) sts_f1(SA_TOT(w), y);
             __syncthreads();
             // post(i)
-            float Z = (lane < NW) ? s_tot[lane] * czl : 0.f;
+            float Z = (lane < NW) ? lds_f1v(SA_TOT(lane)) * czl : 0.f;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) Z += __shfl_xor_sync(0xffffffffu, Z, o);
             const float X = fmaf(Cexcl, Z, yex);  // D(i, first column of the right neighbour)
@@ -373,7 +416,7 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser_kernel(DevEhmm E, DevQue
                 sM[c] = fmaf(pmd[c], dr, Mp[c] + bE);
                 sI[c] = nI[c];
             }
-            if (lane == 0) s_bM[(i & 1) * S_RED + w] = sM[0];
+            if (lane == 0) sts_f1(SA_BM(i & 1, w), sM[0]);
             __syncthreads();
         }
         if (Wk.dbg_bwd != nullptr && tid == 0)

@@ -67,17 +67,6 @@ __host__ __device__ inline WaveLayout wave_layout(int Lcap, int max_strips, int 
     return w;
 }
 
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ float4 lds_f4(unsigned a) {
-    float4 v;
-    asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ float lds_f1(unsigned a) { float v; asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
-__device__ __forceinline__ int lds_u8(unsigned a) { unsigned v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return (int)v; }
-// Opaque identity: stops ptxas/nvcc from rebuilding a cheap-looking address expression inside the step loop
-#define PIN32(x) asm volatile("" : "+r"(x))
-#define PIN64(x) asm volatile("" : "+l"(x))
 // emission odds of C consecutive columns for symbol row at shared address `a` (strip-interleaved layout)
 template <int C>
 __device__ __forceinline__ void lds_emis(unsigned a, float (&e)[C]) {
