@@ -114,6 +114,24 @@ int witch_align_dev(witch_ehmm *e, witch_queries *q, int n_pairs, const int32_t 
                     const int64_t *h_col_offsets, int32_t *d_cols, void *stream);
 
 /*
+ * Weighted alignment-graph merge of one query's per-HMM alignments into a backbone row == the graph build, the
+ * max-weight-trace DP, its backtrace and compressInsertions of alignSubQueriesNew (gcmm/aligner.py:387-495,
+ * helpers/alignment_tools.py:1356-1384), for n_queries queries at once. All arrays are HOST memory.
+ *   qlen[n], res_off[n]: length and offset of each query's residues in `residues` (ASCII, already upper-cased)
+ *   pair_begin[n+1]: the included pairs of query q are pair_begin[q] .. pair_begin[q+1]-1, in decreasing weight
+ *   pair_hmm[np], pair_w[np]: HMM index and weight of each pair; col_off[np], cols: its column list (witch_align)
+ *   hmm_off[H+1], retained[], nongaps[]: per subset, the backbone column and the non-gap count of every retained
+ *       column (subset_to_retained_columns / subset_to_nongaps_per_column, gcmm/algorithm.py:423-429)
+ *   row_off[n]: where query q's row starts in `rows`; capacity needed per query: 2*backbone_length + qlen + 2
+ *   rows, row_len[n]: output characters (upper = aligned, lower = insertion, '-' = gap) and their count
+ *       (0 = the query has no included HMM; the reference returns an empty alignment for it)
+ */
+int witch_graph_align(witch_ehmm *e, int n_queries, const int32_t *qlen, const int64_t *res_off, const char *residues,
+                      const int32_t *pair_begin, const int32_t *pair_hmm, const double *pair_w, const int64_t *col_off,
+                      const int32_t *cols, int n_hmm, const int64_t *hmm_off, const int32_t *retained,
+                      const int32_t *nongaps, int backbone_length, const int64_t *row_off, char *rows, int32_t *row_len);
+
+/*
  * Instrumentation for bench.py: number of kernels this library has launched so far in this process and the
  * accumulated device time (ms, CUDA events on the launching stream) of the dominant DP kernels since the last
  * witch_prof_reset(). Timing is only collected while witch_prof_enable(1).

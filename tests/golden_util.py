@@ -26,6 +26,7 @@ def load_set(name, workdir=None):
     gold = json.load(open(os.path.join(d, "golden.json")))
     queries = read_fasta(os.path.join(d, "queries.fasta"))
     workdir = workdir or tempfile.mkdtemp(prefix="witch_golden_")
+    os.makedirs(workdir, exist_ok=True)
     paths = []
     for h in gold["hmms"]:
         p = os.path.join(workdir, name + "_" + h["file"][:-3])

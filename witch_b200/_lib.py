@@ -31,6 +31,8 @@ SYMBOLS = {
     "witch_weights_topk_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "witch_align": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, c_i32p, c_i32p, c_i64p, c_i32p]),
     "witch_align_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, c_i32p, c_i32p, c_i64p, ctypes.c_void_p, ctypes.c_void_p]),
+    "witch_graph_align": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_i32p, c_i64p, ctypes.c_char_p, c_i32p, c_i32p, c_f64p, c_i64p,
+                                         c_i32p, ctypes.c_int, c_i64p, c_i32p, c_i32p, ctypes.c_int, c_i64p, ctypes.c_void_p, c_i32p]),
     "witch_kernel_launches": (ctypes.c_uint64, []),
     "witch_prof_enable": (None, [ctypes.c_int]),
     "witch_prof_reset": (None, []),

@@ -134,6 +134,47 @@ def align(ehmm, queries, qidx, hidx):
     return [cols[off[p]:off[p + 1]] for p in range(len(qidx))]
 
 
+def graph_align(ehmm, seqs, pair_begin, pair_hmm, pair_w, cols_list, retained_columns, nongaps_per_column, backbone_length):
+    """Weighted alignment-graph merge for many queries (gcmm/aligner.py:387-495 + compressInsertions).
+    seqs: upper-case query strings; pair_begin[n+1]; pair_hmm/pair_w/cols_list per included pair (decreasing weight
+    within a query); retained_columns / nongaps_per_column: per-subset int sequences. -> list of row strings
+    ('' where the query has no included HMM)."""
+    n = len(seqs)
+    qlen = np.array([len(s) for s in seqs], dtype=np.int32)
+    res_off = np.zeros(n, dtype=np.int64)
+    if n:
+        res_off[1:] = np.cumsum(qlen[:-1])
+    blob = "".join(seqs).encode()
+    pair_begin = np.ascontiguousarray(pair_begin, dtype=np.int32)
+    pair_hmm = np.ascontiguousarray(pair_hmm, dtype=np.int32)
+    pair_w = np.ascontiguousarray(pair_w, dtype=np.float64)
+    col_off = np.zeros(max(len(cols_list), 1), dtype=np.int64)
+    if cols_list:
+        col_off[1:len(cols_list)] = np.cumsum([len(c) for c in cols_list[:-1]])
+        cols = np.ascontiguousarray(np.concatenate([np.asarray(c, dtype=np.int32) for c in cols_list]), dtype=np.int32)
+    else:
+        cols = np.zeros(1, dtype=np.int32)
+    H = len(retained_columns)
+    hmm_off = np.zeros(H + 1, dtype=np.int64)
+    np.cumsum([len(r) for r in retained_columns], out=hmm_off[1:])
+    ret = np.ascontiguousarray(np.concatenate([np.asarray(r, dtype=np.int32) for r in retained_columns]), dtype=np.int32)
+    ng = np.ascontiguousarray(np.concatenate([np.asarray(r, dtype=np.int32) for r in nongaps_per_column]), dtype=np.int32)
+    cap = 2 * backbone_length + qlen.astype(np.int64) + 2
+    row_off = np.zeros(n, dtype=np.int64)
+    if n:
+        row_off[1:] = np.cumsum(cap[:-1])
+    rows = ctypes.create_string_buffer(int(cap.sum()) + 1)
+    row_len = np.zeros(n, dtype=np.int32)
+    if n:
+        check(_lib.load().witch_graph_align(
+            ehmm._h, n, _ptr(qlen, ctypes.c_int32), _ptr(res_off, ctypes.c_int64), blob, _ptr(pair_begin, ctypes.c_int32),
+            _ptr(pair_hmm, ctypes.c_int32), _ptr(pair_w, ctypes.c_double), _ptr(col_off, ctypes.c_int64),
+            _ptr(cols, ctypes.c_int32), H, _ptr(hmm_off, ctypes.c_int64), _ptr(ret, ctypes.c_int32), _ptr(ng, ctypes.c_int32),
+            int(backbone_length), _ptr(row_off, ctypes.c_int64), rows, _ptr(row_len, ctypes.c_int32)))
+    raw = rows.raw
+    return [raw[row_off[q]:row_off[q] + row_len[q]].decode() for q in range(n)]
+
+
 def debug_fwdbwd(ehmm, queries, qidx, hidx, multihit):
     qidx = np.ascontiguousarray(qidx, dtype=np.int32)
     hidx = np.ascontiguousarray(hidx, dtype=np.int32)

@@ -324,3 +324,73 @@ extern "C" double witch_measure_fp32_peak(double ms_target) {
         return -1.0;
     }
 }
+
+extern "C" int witch_graph_align(witch_ehmm *e, int nq, const int32_t *qlen, const int64_t *res_off, const char *residues,
+                                 const int32_t *pair_begin, const int32_t *pair_hmm, const double *pair_w,
+                                 const int64_t *col_off, const int32_t *cols, int n_hmm, const int64_t *hmm_off,
+                                 const int32_t *retained, const int32_t *nongaps, int backbone_length,
+                                 const int64_t *row_off, char *rows, int32_t *row_len) {
+    try {
+        if (!e || nq < 0 || (nq > 0 && (!qlen || !res_off || !residues || !pair_begin || !hmm_off || !retained || !nongaps ||
+                                        !row_off || !rows || !row_len)) || backbone_length <= 0 || n_hmm <= 0)
+            return fail(WITCH_ERR_ARG, "witch_graph_align: bad arguments");
+        if (nq == 0) return WITCH_OK;
+        CUDA_TRY(cudaSetDevice(e->device));
+        const int np = pair_begin[nq];
+        int Lcap = 1;
+        long long res_total = 0, cols_total = 0, rows_total = 0;
+        for (int q = 0; q < nq; q++) {
+            Lcap = std::max(Lcap, qlen[q]);
+            res_total = std::max<long long>(res_total, res_off[q] + qlen[q]);
+            rows_total = std::max<long long>(rows_total, row_off[q] + 2LL * backbone_length + qlen[q] + 2);
+            if (pair_begin[q + 1] - pair_begin[q] > GRAPH_KMAX) return fail(WITCH_ERR_LIMIT, "more than 16 included HMMs for one query");
+            for (int p = pair_begin[q]; p < pair_begin[q + 1]; p++) {
+                if (pair_hmm[p] < 0 || pair_hmm[p] >= n_hmm) return fail(WITCH_ERR_ARG, "witch_graph_align: HMM index out of range");
+                cols_total = std::max<long long>(cols_total, col_off[p] + qlen[q]);
+            }
+        }
+        auto up = [&](auto &buf, const auto *src, size_t n) {
+            buf.alloc(n);
+            if (n) CUDA_TRY(cudaMemcpy(buf.p, src, n * sizeof(*src), cudaMemcpyHostToDevice));
+        };
+        DevBuf<int> d_qlen, d_pb, d_ph, d_cols, d_ret, d_ng, d_rl;
+        DevBuf<long long> d_ro, d_co, d_ho, d_rowoff;
+        DevBuf<double> d_pw;
+        DevBuf<char> d_res, d_rows;
+        std::vector<long long> ro(res_off, res_off + nq), co(col_off, col_off + std::max(np, 0)), ho(hmm_off, hmm_off + n_hmm + 1),
+            rwo(row_off, row_off + nq);
+        up(d_qlen, qlen, nq); up(d_ro, ro.data(), nq); up(d_res, residues, (size_t)res_total);
+        up(d_pb, pair_begin, nq + 1); up(d_ph, pair_hmm, np); up(d_pw, pair_w, np); up(d_co, co.data(), np);
+        up(d_cols, cols, (size_t)cols_total); up(d_ho, ho.data(), n_hmm + 1);
+        up(d_ret, retained, (size_t)hmm_off[n_hmm]); up(d_ng, nongaps, (size_t)hmm_off[n_hmm]);
+        up(d_rowoff, rwo.data(), nq);
+        d_rows.alloc((size_t)rows_total); d_rl.alloc(nq);
+        const int Wcap = backbone_length + 3;
+        const long long nblocks = Lcap / 32 + 2, nw16 = (Wcap + 31) / 16 + 2;
+        long long slot = (long long)Wcap * 8 + (long long)Lcap * GRAPH_KMAX * 12 + (long long)Lcap * 4 +
+                         ((Lcap + Wcap + 15) / 16) * 16 + nblocks * nw16 * 32 * 4;
+        slot = (slot + 255) / 256 * 256;
+        int occ = 1;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, graph_dp_kernel, 128, 0));
+        long long grid = std::min<long long>(((long long)nq + 3) / 4, (long long)e->num_sms * std::max(occ, 1));
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        grid = std::max<long long>(1, std::min<long long>(grid, (long long)(0.5 * free_b / (4.0 * slot))));
+        DevBuf<char> scratch; scratch.alloc((size_t)grid * 4 * slot);
+        e->counter.alloc(64);
+        CUDA_TRY(cudaMemset(e->counter.p, 0, sizeof(unsigned)));
+        GraphWork G;
+        G.nq = nq; G.qlen = d_qlen.p; G.res_off = d_ro.p; G.residues = d_res.p; G.pair_begin = d_pb.p; G.pair_hmm = d_ph.p;
+        G.pair_w = d_pw.p; G.col_off = d_co.p; G.cols = d_cols.p; G.hmm_off = d_ho.p; G.retained = d_ret.p; G.nongaps = d_ng.p;
+        G.backbone_length = backbone_length; G.row_off = d_rowoff.p; G.rows = d_rows.p; G.row_len = d_rl.p;
+        G.counter = e->counter.p; G.scratch = scratch.p; G.slot_bytes = slot; G.Lcap = Lcap;
+        graph_dp_kernel<<<(int)grid, 128>>>(G);
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpy(rows, d_rows.p, (size_t)rows_total, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(row_len, d_rl.p, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost));
+        return WITCH_OK;
+    } catch (const std::exception &ex) {
+        return fail(WITCH_ERR_CUDA, ex.what());
+    }
+}

@@ -17,6 +17,7 @@
 #include "parser_kernel.cuh"
 #include "wave_kernels.cuh"
 #include "post_kernels.cuh"
+#include "graph_kernel.cuh"
 
 using namespace witch;
 

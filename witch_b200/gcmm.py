@@ -55,6 +55,7 @@ class BatchedSearch:
         """SearchAlgorithm.search: returns nothing in the reference (results go to files); here the device score
         table is kept on `self` and also returned as numpy: (scores[n,H], reported[n,H])."""
         self.taxa = list(taxa)
+        self._seqs = list(seqs)
         self.queries = api.Queries(self.ehmm, seqs)
         scores, rep, pre, flags = api.score(self.ehmm, self.queries)
         self.scores, self.reported, self.pre, self.flags = scores, rep, pre, flags
@@ -124,6 +125,34 @@ class BatchedSearch:
         for t, h, c in zip(owner, ph, cols):
             out[t][2][h] = [int(x) for x in c]
         return out
+
+
+    def alignSubQueriesNew(self, backbone_length, subset_to_retained_columns, subset_to_nongaps_per_column,
+                           taxon_to_weights=None):
+        """Batched alignSubQueriesNew (gcmm/aligner.py:350-538) for every query: adaptive inclusion, device alignment
+        of the kept (query, HMM) pairs, device weighted alignment-graph DP + backtrace + compressInsertions.
+        -> {taxon: row string} (upper = aligned to a backbone column, lower = insertion, '-' = gap); queries
+        without weights are absent (the reference returns an empty ExtendedAlignment for them)."""
+        bb = self.getBackbones(taxon_to_weights)
+        seqs, pair_begin, pair_hmm, pair_w, cols, taxa = [], [0], [], [], [], []
+        name_to_q = {t: q for q, t in enumerate(self.taxa)}
+        for t, v in bb.items():
+            if v[0] == "N/A":
+                continue
+            _, wmap, s2c = v
+            taxa.append(t)
+            seqs.append(self._seq_upper(name_to_q[t]))
+            for h, c in s2c.items():        # insertion order == decreasing weight (getBackbones)
+                pair_hmm.append(h); pair_w.append(wmap[h]); cols.append(c)
+            pair_begin.append(len(pair_hmm))
+        H = self.ehmm.n
+        ret = [subset_to_retained_columns[h] for h in range(H)]
+        ng = [subset_to_nongaps_per_column[h] for h in range(H)]
+        rows = api.graph_align(self.ehmm, seqs, pair_begin, pair_hmm, pair_w, cols, ret, ng, backbone_length)
+        return {t: r for t, r in zip(taxa, rows) if r}
+
+    def _seq_upper(self, q):
+        return self._seqs[q].upper()
 
 
 def writeWeightsToLocal(taxon_to_weights, path):
