@@ -270,10 +270,10 @@ def graph_align(seq, backbone_length, subset_to_weight, subset_to_aligned_column
         for i, c in enumerate(cols):
             if c == -1:
                 continue
-            j = retained_columns[subset][c]
+            j = int(retained_columns[subset][c])
             ci.append(i)
             cj.append(j)
-            cw.append(nongaps_per_column[subset][c] * subset_to_weight[subset])
+            cw.append(int(nongaps_per_column[subset][c]) * subset_to_weight[subset])
             min_col, max_col = min(min_col, j), max(max_col, j)
     L = len(seq)
     ci = np.array(ci, dtype=np.int32)
@@ -281,7 +281,7 @@ def graph_align(seq, backbone_length, subset_to_weight, subset_to_aligned_column
     cw = np.array(cw, dtype=np.float64)
     buf = ctypes.create_string_buffer(L + backbone_length + 8)
     i32 = ctypes.POINTER(ctypes.c_int32)
-    n = lib().orc_graph_dp(L, min_col, max_col, len(ci), ci.ctypes.data_as(i32), cj.ctypes.data_as(i32),
+    n = lib().orc_graph_dp(int(L), int(min_col), int(max_col), len(ci), ci.ctypes.data_as(i32), cj.ctypes.data_as(i32),
                            cw.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), buf)
     ops = buf.raw[:n].decode()
     out, i = [], 0
