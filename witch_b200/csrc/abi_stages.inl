@@ -5,19 +5,20 @@ static int wave_C_for(const witch_ehmm *) { return 8; }
 struct WaveBucket { int Lcap; std::vector<WaveItem> items; };
 
 // Launches the wavefront kernel over `items` (any order); outputs indexed by WaveItem::pair.
-template <bool ALIGN>
-static void run_wave(witch_ehmm *e, witch_queries *q, std::vector<WaveItem> items, float *d_envsc, float *d_domcorr,
+template <bool ALIGN, int C, int WAVE_WARPS, int MINB, int RING>
+static void run_wave_c(witch_ehmm *e, witch_queries *q, std::vector<WaveItem> items, float *d_envsc, float *d_domcorr,
                      int *d_cols, const long long *d_coloff, float *d_dbg_fwd, float *d_dbg_bwd, cudaStream_t st) {
     if (items.empty()) return;
-    constexpr int C = 8;
     const int SW = 32 * C;
     // buckets by envelope length so that scratch is not sized by the single longest item
     const int caps[] = {256, 512, 1024, 2048, 4096, 1 << 30};
-    std::vector<WaveBucket> buckets(6);
+    // ... and by model size class, so that the shared-memory emission table of the few long models (the root of the
+    // decomposition holds every backbone column) does not set the occupancy of everything else
+    std::vector<WaveBucket> buckets(12);
     for (auto &it : items) {
         int b = 0;
         while (it.Ls > caps[b]) b++;
-        buckets[b].items.push_back(it);
+        buckets[2 * b].items.push_back(it);
     }
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
@@ -45,9 +46,11 @@ static void run_wave(witch_ehmm *e, witch_queries *q, std::vector<WaveItem> item
         }
         const WaveLayout lay = wave_layout(Lcap, max_strips, C, ALIGN);
         const int emis_floats = q->nsym * max_strips * SW;
-        const size_t smem = (size_t)emis_floats * sizeof(float) + (size_t)WAVE_WARPS * W_RES_CAP;
-        if (smem > 200 * 1024) throw std::runtime_error("emission table does not fit shared memory");
-        auto kern = wave_kernel<C, ALIGN>;
+        const int res_cap = (Lcap + 1 + 15) / 16 * 16;
+        const size_t smem = (size_t)emis_floats * sizeof(float) + (size_t)WAVE_WARPS * res_cap +
+                            (size_t)WAVE_WARPS * RING * (wave_ring_stage_bytes(C, ALIGN) + 8);
+        if (smem > 220 * 1024) throw std::runtime_error("emission table + residue staging do not fit shared memory");
+        auto kern = wave_kernel<C, ALIGN, WAVE_WARPS, MINB, RING>;
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 1;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WAVE_WARPS * 32, smem));
@@ -64,7 +67,7 @@ static void run_wave(witch_ehmm *e, witch_queries *q, std::vector<WaveItem> item
         WaveWork wk;
         wk.items = ditems.p; wk.group_first = dgf.p; wk.group_count = dgc.p; wk.ngroups = (int)gfirst.size();
         wk.counter = e->counter.p; wk.scratch = (char *)e->bytes.p; wk.slot_bytes = lay.total; wk.Lcap = Lcap;
-        wk.max_strips = max_strips; wk.emis_floats = emis_floats; wk.envsc = d_envsc; wk.domcorr = d_domcorr; wk.cols = d_cols; wk.col_off = d_coloff;
+        wk.max_strips = max_strips; wk.emis_floats = emis_floats; wk.res_cap = res_cap; wk.envsc = d_envsc; wk.domcorr = d_domcorr; wk.cols = d_cols; wk.col_off = d_coloff;
         wk.dbg_fwd = d_dbg_fwd; wk.dbg_bwd = d_dbg_bwd;
         {
             ScopedTimer tm(ALIGN ? 2 : 1, st, cells);
@@ -74,6 +77,15 @@ static void run_wave(witch_ehmm *e, witch_queries *q, std::vector<WaveItem> item
         }
         CUDA_TRY(cudaStreamSynchronize(st));  // ditems/dgf/dgc are freed at scope exit
     }
+}
+
+template <bool ALIGN>
+static void run_wave(witch_ehmm *e, witch_queries *q, std::vector<WaveItem> items, float *d_envsc, float *d_domcorr,
+                     int *d_cols, const long long *d_coloff, float *d_dbg_fwd, float *d_dbg_bwd, cudaStream_t st) {
+#define WV_ARGS e, q, std::move(items), d_envsc, d_domcorr, d_cols, d_coloff, d_dbg_fwd, d_dbg_bwd, st
+    if (ALIGN) run_wave_c<true, 8, 4, 2, 3>(WV_ARGS);
+    else run_wave_c<false, 8, 4, 3, 3>(WV_ARGS);
+#undef WV_ARGS
 }
 
 static void check_handles(witch_ehmm *e, witch_queries *q) {

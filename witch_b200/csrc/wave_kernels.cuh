@@ -11,6 +11,7 @@
 // which visits tile row t = L+31-t', reads them back fully coalesced for posterior decoding.
 // Scaling: one power-of-two exponent per warp and step (exact integer bookkeeping), renormalised every 8 steps.
 #pragma once
+#include <type_traits>
 #include "device_types.cuh"
 #include "parser_kernel.cuh"
 
@@ -34,6 +35,7 @@ struct WaveWork {
     int Lcap;       // max Ls in this launch
     int max_strips;
     int emis_floats;  // floats reserved for the emission table in dynamic shared memory (residue staging follows)
+    int res_cap;      // bytes of residue staging per warp (multiple of 16, >= Lcap + 1)
     // outputs (envelope mode)
     float *envsc;   // [nitems] ln P(envelope | unihit model)
     float *domcorr; // [nitems] sum of ln null2 over the envelope
@@ -43,9 +45,36 @@ struct WaveWork {
     float *dbg_fwd, *dbg_bwd;  // optional per item totals (nats)
 };
 
-constexpr int WAVE_WARPS = 4;  // warps per CTA (they share one HMM's emission table in shared memory)
+constexpr int WAVE_WARPS_MAX = 8;  // warps per CTA (they share one HMM's emission table in shared memory)
+
 constexpr int W_SCALE_EVERY = 8;
-constexpr int W_RES_CAP = 4096;  // residues of one item staged in shared memory per warp (longer items read HBM)
+__host__ __device__ constexpr int wave_ring_stage_bytes(int C, bool align) { return 32 * C * 4 * (align ? 2 : 1); }
+// ---- TMA (1-D bulk async copy) + mbarrier: completion is tracked in shared memory, not on a register scoreboard
+__device__ __forceinline__ void mbar_init(unsigned bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ float4 lds_f4v(unsigned a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
 
 // scratch layout helper (all offsets in bytes, per warp slot)
 struct WaveLayout {
@@ -87,9 +116,11 @@ __device__ __forceinline__ bool oa_e_better(float v2, int d2, int o2, float v1, 
     return d2 == 0 ? (o2 > o1) : (o2 < o1);  // last M in visiting order, first D in visiting order
 }
 
-template <int C, bool ALIGN>
-__global__ void __launch_bounds__(WAVE_WARPS * 32, ALIGN ? 2 : 3) wave_kernel(DevEhmm E, DevQueries Q, WaveWork Wk) {
+template <int C, bool ALIGN, int WAVE_WARPS, int MINB, int W_RING>
+__global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, DevQueries Q, WaveWork Wk) {
     extern __shared__ float smem[];
+    static_assert(W_RING >= 2, "the Backward sweep reads stored Forward rows through the TMA ring");
+    constexpr bool RING = true;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     __shared__ int s_group;
     __shared__ float s_n2[WAVE_WARPS][MAX_SYM];
@@ -110,6 +141,7 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, ALIGN ? 2 : 3) wave_kernel(De
 #define BND_D(i) bnd[8 * (i) + 2]
 #define BND_E(i) bnd[8 * (i) + 3]
 #define BND_G(i) bndi[8 * (i) + 4]
+#define BND_V(i) (*reinterpret_cast<float4 *>(bnd + 8 * (i)))  // {M, I, D, E} of one record as one 128-bit access
     float *rFC = (float *)(slot + lay.rows);
     int *rFCg = (int *)(rFC + LB);
     float *rNB = (float *)(rFCg + LB);
@@ -121,6 +153,19 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, ALIGN ? 2 : 3) wave_kernel(De
     const unsigned emis_sa = smem_u32(emis_s);
     const int SW = 32 * C;  // strip width
 
+    // ring state persists across strips and items (the mbarriers are initialised once; phases keep alternating)
+    int rd_stage = 0, wr_stage = 0;
+    unsigned rd_phase = 0;
+    if (RING) {
+        constexpr int RSB0 = wave_ring_stage_bytes(C, ALIGN);
+        const unsigned bar0 = emis_sa + Wk.emis_floats * 4 + WAVE_WARPS * Wk.res_cap + WAVE_WARPS * (W_RING * RSB0) + w * (W_RING * 8);
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < W_RING; k++) mbar_init(bar0 + k * 8, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
     int loaded_h = -1, Mstr = 0;
     for (;;) {
         __syncthreads();
@@ -149,14 +194,19 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, ALIGN ? 2 : 3) wave_kernel(De
         const WaveItem it = Wk.items[gfirst + w];
         const int Ls = it.Ls, Lfull = Q.len[it.q];
         const uint8_t *dsq = Q.dsq + Q.off[it.q] + (it.i0 - 1);  // dsq[i-1] = residue i of the envelope
-        const bool staged = it.Ls <= W_RES_CAP;
-        const unsigned sres = emis_sa + Wk.emis_floats * 4 + w * W_RES_CAP;
-        if (staged) {  // stage the item's residues in shared memory (one byte each)
-            uint8_t *sr = reinterpret_cast<uint8_t *>(emis_s + Wk.emis_floats) + w * W_RES_CAP;
+        // the item's residues are staged in shared memory (one byte each; the launch sizes res_cap >= Lcap + 1)
+        const unsigned sres = emis_sa + Wk.emis_floats * 4 + w * Wk.res_cap;
+        {
+            uint8_t *sr = reinterpret_cast<uint8_t *>(emis_s + Wk.emis_floats) + w * Wk.res_cap;
             for (int z = lane; z < it.Ls; z += 32) sr[z] = dsq[z];
             __syncwarp();
         }
-#define RES_AT(idx) (staged ? lds_u8(sresp + (idx)) : (int)dsq[(idx)])
+#define RES_AT(idx) lds_u8(sresp + (idx))
+        // this warp's ring of stored Forward rows: [stage][M|I][v][lane][4 floats]  (conflict-free LDS.128)
+        constexpr int RSB = wave_ring_stage_bytes(C, ALIGN);
+        const unsigned ring_w = emis_sa + Wk.emis_floats * 4 + WAVE_WARPS * Wk.res_cap + w * (W_RING * RSB);
+        const unsigned ring_sa = ring_w + lane * 16;
+        const unsigned ring_bar = emis_sa + Wk.emis_floats * 4 + WAVE_WARPS * Wk.res_cap + WAVE_WARPS * (W_RING * RSB) + w * (W_RING * 8);
         const long long po = E.poff[h];
         const float pmove = 2.0f / ((float)Lfull + 2.0f), ploop = 1.0f - pmove;
         const unsigned FULL = 0xffffffffu;
@@ -184,36 +234,42 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, ALIGN ? 2 : 3) wave_kernel(De
             unsigned ebase = emis_sa + (s * SW + lane * 4) * 4;
             unsigned erow = Mstr * 4;
             float *tM = tileM + (size_t)s * TT * SW, *tI = tileI + (size_t)s * TT * SW;
-            int toff = (32 + lane) * C;  // element offset of (step t, lane) in the strip's wave-layout tile
+            // wave-layout tile of a strip: [step t][v][lane][4 floats] -- every 128-bit access of a warp is one
+            // contiguous 512-byte run (v-th quad of the lane's C columns)
+            int toff = 32 * C + lane * 4;  // element offset of (step t, lane) quad 0
             int *gFs = gFarr + s * TG;
             unsigned sresp = sres;
             PIN32(ebase); PIN32(erow); PIN64(tM); PIN64(gFs); PIN32(sresp);
             if (ALIGN) PIN64(tI);
             if (last) { xCv = 0.f; xCg = g; }
             int xcur = RES_AT(min(max(-lane, 0), Ls - 1));  // residue of the lane's row at the next step
-            float pbM = 0.f, pbI = 0.f, pbD = 0.f, pbE = 0.f;  // strip boundary of lane 0's next row (prefetched)
+            float4 pbv = make_float4(0.f, 0.f, 0.f, 0.f);  // strip boundary {M,I,D,E} of lane 0's next row (prefetched)
             int pbG = 0;
-            if (s > 0) { pbM = BND_M(1); pbI = BND_I(1); pbD = BND_D(1); pbE = BND_E(1); pbG = BND_G(1); }
-            for (int t = 1; t <= nsteps; t++) {
+            if (s > 0) { pbv = BND_V(1); pbG = BND_G(1); }
+            int aheadG = (s > 0) ? BND_G(min(Ls, 2 * W_SCALE_EVERY)) : 0;  // exponent the left strip had one block ahead (prefetched)
+            float *tMp = tM + toff, *tIp = tI + toff;  // running tile pointers of the current step
+            // One wavefront step. ALL = every lane is inside the sequence (steady state: no activity predicate, no clamps).
+            auto fstep = [&](const int t, auto allc) {
+                constexpr bool ALL = decltype(allc)::value;
                 const int i = t - lane;
-                const bool act = (i >= 1 && i <= Ls);
+                const bool act = ALL || (i >= 1 && i <= Ls);
                 // values of row i at the column left of my block: left lane's last step, or the strip boundary
                 float cM = __shfl_up_sync(FULL, sM[C - 1], 1);
                 float cI = __shfl_up_sync(FULL, sI[C - 1], 1);
                 float cD = __shfl_up_sync(FULL, sD[C - 1], 1);
                 float cE = __shfl_up_sync(FULL, ep, 1);
-                if (lane == 0) {
-                    if (s > 0 && act) {
-                        const float f = pow2i(pbG - g);
-                        cM = pbM * f; cI = pbI * f; cD = pbD * f; cE = pbE * f;
-                    } else { cM = 0.f; cI = 0.f; cD = 0.f; cE = 0.f; }
+                {   // lane 0: strip boundary of the left strip, or zeros (first strip / outside the sequence); branch-free
+                    float f = 0.f;
+                    if (s > 0) f = act ? pow2i(pbG - g) : 0.f;
+                    const float bM = pbv.x * f, bI = pbv.y * f, bD = pbv.z * f, bE = pbv.w * f;
+                    cM = lane == 0 ? bM : cM; cI = lane == 0 ? bI : cI; cD = lane == 0 ? bD : cD; cE = lane == 0 ? bE : cE;
                 }
                 if (s > 0) {  // prefetch the boundary of row t+1 (uniform address, consumed by lane 0 next step)
                     const int ib = min(t + 1, Ls);
-                    pbM = BND_M(ib); pbI = BND_I(ib); pbD = BND_D(ib); pbE = BND_E(ib); pbG = BND_G(ib);
+                    pbv = BND_V(ib); pbG = BND_G(ib);
                 }
                 const int xres = xcur;
-                xcur = RES_AT(min(max(i, 0), Ls - 1));
+                xcur = RES_AT(ALL ? i : min(max(i, 0), Ls - 1));
                 if (act) {
                     float e[C];
                     lds_emis<C>(ebase + xres * erow, e);
@@ -236,21 +292,16 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, ALIGN ? 2 : 3) wave_kernel(De
                     rM = cM; rI = cI; rD = cD;
                     xBs *= ploop;
                     // keep the row for posterior decoding (wave layout)
-                    float *dm = tM + toff, *di = tI + toff;
+                    float *dm = tMp, *di = tIp;
                     // (envelope mode needs match posteriors only: sum over emitting states of a row's posteriors is 1,
                     //  so fI + fNCJ = 1 - sum_k fM(k); insert rows are stored for the align stage only)
-                    if (C % 4 == 0) {
 #pragma unroll
-                        for (int v = 0; v < C / 4; v++) {
-                            reinterpret_cast<float4 *>(dm)[v] = make_float4(nM[4 * v], nM[4 * v + 1], nM[4 * v + 2], nM[4 * v + 3]);
-                            if (ALIGN) reinterpret_cast<float4 *>(di)[v] = make_float4(nI[4 * v], nI[4 * v + 1], nI[4 * v + 2], nI[4 * v + 3]);
-                        }
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < C; c++) { dm[c] = nM[c]; if (ALIGN) di[c] = nI[c]; }
+                    for (int v = 0; v < C / 4; v++) {
+                        *reinterpret_cast<float4 *>(dm + 128 * v) = make_float4(nM[4 * v], nM[4 * v + 1], nM[4 * v + 2], nM[4 * v + 3]);
+                        if (ALIGN) *reinterpret_cast<float4 *>(di + 128 * v) = make_float4(nI[4 * v], nI[4 * v + 1], nI[4 * v + 2], nI[4 * v + 3]);
                     }
                     if (lane == 31) {
-                        if (!last) { BND_M(i) = sM[C - 1]; BND_I(i) = sI[C - 1]; BND_D(i) = sD[C - 1]; BND_E(i) = ep; BND_G(i) = g; }
+                        if (!last) { BND_V(i) = make_float4(sM[C - 1], sI[C - 1], sD[C - 1], ep); BND_G(i) = g; }
                         else {
                             // C(i) = C(i-1)*loop + E(i)   (unihit: E->C = 1), with exponent alignment
                             const float f = pow2i(xCg - g);
@@ -259,9 +310,13 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, ALIGN ? 2 : 3) wave_kernel(De
                         }
                     }
                 }
-                toff += 32 * C;
-                if (((t - 1) & 7) == 0 && lane == 0) gFs[(t - 1) >> 3] = g;  // exponent of steps t .. t+7
-                if ((t & (W_SCALE_EVERY - 1)) == 0) {
+                tMp += 32 * C;
+                if (ALIGN) tIp += 32 * C;
+            };
+            // every 8 steps: record the exponent of the block (for the Backward pass) / renormalise
+            auto fmark = [&](const int t) { if (lane == 0) gFs[(t - 1) >> 3] = g; };  // exponent of steps t .. t+7
+            auto frescale = [&](const int t) {
+                {
                     float mx = 0.f;
 #pragma unroll
                     for (int c = 0; c < C; c++) mx = fmaxf(mx, fmaxf(sM[c], fmaxf(sI[c], sD[c])));
@@ -270,8 +325,9 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, ALIGN ? 2 : 3) wave_kernel(De
                     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
                     int e_need = (mx > 1048576.f) ? fexp(mx) : 0;
                     if (s > 0) {
-                        int ahead = BND_G(min(Ls, t + W_SCALE_EVERY)) - 40 - g;
+                        const int ahead = aheadG - 40 - g;
                         e_need = max(e_need, ahead);
+                        aheadG = BND_G(min(Ls, t + 2 * W_SCALE_EVERY));
                     }
                     if (e_need > 0) {
                         const float f = pow2i(-e_need);
@@ -280,6 +336,27 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, ALIGN ? 2 : 3) wave_kernel(De
                         for (int c = 0; c < C; c++) { sM[c] *= f; sI[c] *= f; sD[c] *= f; }
                         rM *= f; rI *= f; rD *= f; ep *= f; xBs *= f;
                     }
+                }
+            };
+            {
+                const std::integral_constant<bool, false> genc;
+                const std::integral_constant<bool, true> allc;
+                int t = 1;
+                for (; t <= 32; t++) {   // ramp-up (nsteps = Ls + 31 >= 32)
+                    if (((t - 1) & 7) == 0) fmark(t);
+                    fstep(t, genc);
+                    if ((t & (W_SCALE_EVERY - 1)) == 0) frescale(t);
+                }
+                for (; t + 7 <= Ls; t += 8) {   // steady state: all 32 lanes inside the sequence, blocks of 8 steps
+                    fmark(t);
+#pragma unroll 1
+                    for (int u = 0; u < 8; u++) fstep(t + u, allc);
+                    frescale(t + 7);
+                }
+                for (; t <= nsteps; t++) {   // drain
+                    if (((t - 1) & 7) == 0) fmark(t);
+                    fstep(t, genc);
+                    if ((t & (W_SCALE_EVERY - 1)) == 0) frescale(t);
                 }
             }
             if (last) {
@@ -327,62 +404,68 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, ALIGN ? 2 : 3) wave_kernel(De
             if (ALIGN) PIN64(tI);
             if (firstS) { xNv = 0.f; xNg = g; }
             int xcur = RES_AT(Ls - 1);  // residue i+1 of the lane's row at the next step
-            float pbM = 0.f, pbD = 0.f, pbE = 0.f;
+            float4 pbv = make_float4(0.f, 0.f, 0.f, 0.f);  // strip boundary {M,-,D,B} of lane 31's next row (prefetched)
             int pbG = 0;
-            if (!lastS) { pbM = BND_M(Ls); pbD = BND_D(Ls); pbE = BND_E(Ls); pbG = BND_G(Ls); }
-            float FMn[C], FIn[C];  // forward row of the next step (prefetched)
-            int toff = ((Ls + 31) * 32 + lane) * C;  // tile element offset of the forward row matching the current step
-            int gFc = gFs[(Ls + 30) >> 3];
+            if (!lastS) { pbv = BND_V(Ls); pbG = BND_G(Ls); }
+            int aheadG = lastS ? 0 : BND_G(max(0, Ls - (2 * W_SCALE_EVERY - 1)));  // right strip's exponent one block ahead
+            int gblk = (Ls + 30) >> 3;
+            int gFc = gFs[gblk];
+            int gFnext = gFs[max(gblk - 1, 0)];      // exponent of the next (earlier) block of forward steps, prefetched
             float fac = exp2f((float)(gFc + g - gT)) * invT;  // posterior scale; refreshed when an exponent changes
-            {
-                const float *fm = tM + toff, *fi = tI + toff;
+            // Stored Forward rows come back through a shared-memory ring filled by TMA bulk copies, W_RING-1 steps ahead
+            // of their use (one lane issues one copy per step: the step's rows of all 32 lanes are one contiguous run;
+            // completion is an mbarrier transaction count, so no register scoreboard is tied up by the prefetch).
+            const float *tMrd = tM + (size_t)(Ls + 31) * 32 * C;   // rows of step 0; step tq is 32*C floats earlier
+            const float *tIrd = tI + (size_t)(Ls + 31) * 32 * C;
+            float *tMw = tM + (size_t)(Ls + 31) * 32 * C + lane * 4, *tIw = tI + (size_t)(Ls + 31) * 32 * C + lane * 4;
+            int tq_next = 0;   // next step whose rows have not been requested yet
+            auto ring_issue = [&]() {
+                if (lane == 0) {
+                    const unsigned dst = ring_w + wr_stage * RSB, bar = ring_bar + wr_stage * 8;
+                    mbar_expect_tx(bar, RSB);
+                    tma_load_1d(dst, tMrd, 32 * C * 4, bar);
+                    if (ALIGN) tma_load_1d(dst + 32 * C * 4, tIrd, 32 * C * 4, bar);
+                }
+                tMrd -= 32 * C;
+                if (ALIGN) tIrd -= 32 * C;
+                wr_stage = (wr_stage == W_RING - 1) ? 0 : wr_stage + 1;
+                tq_next++;
+            };
+            fence_proxy_async();  // this warp's generic-proxy writes of the tile are ordered before the TMA reads
+            __syncwarp();
 #pragma unroll
-                for (int c = 0; c < C; c++) { FMn[c] = fm[c]; FIn[c] = ALIGN ? fi[c] : 0.f; }
-            }
-            for (int tp = 0; tp < nstepsB; tp++) {
+            for (int k = 0; k < W_RING - 1; k++) ring_issue();   // nstepsB >= 32 > W_RING
+
+            // One wavefront step. ALL = every lane has 1 <= i < Ls (steady state: no predicates, no clamps).
+            auto bstep = [&](const int tp, auto allc) {
+                constexpr bool ALL = decltype(allc)::value;
                 const int i = Ls - (tp - (31 - lane));
-                const bool act = (i >= 0 && i <= Ls);
+                const bool act = ALL || (i >= 0 && i <= Ls);
                 float cMb = __shfl_down_sync(FULL, sM[0], 1);   // Mb(i, right column)   (row i of the right lane)
                 float cDb = __shfl_down_sync(FULL, sD[0], 1);   // Db(i, right column)
                 float cB = __shfl_down_sync(FULL, bp, 1);
-                if (lane == 31) {
-                    if (!lastS && act) {
-                        const float f = pow2i(pbG - g);
-                        cMb = pbM * f; cDb = pbD * f; cB = pbE * f;
-                    } else { cMb = 0.f; cDb = 0.f; cB = 0.f; }
+                {   // lane 31: boundary of the strip to the right, or zeros (last strip / outside the sequence); branch-free
+                    float f = 0.f;
+                    if (!lastS) f = act ? pow2i(pbG - g) : 0.f;
+                    const float bM = pbv.x * f, bD = pbv.z * f, bB = pbv.w * f;
+                    cMb = lane == 31 ? bM : cMb; cDb = lane == 31 ? bD : cDb; cB = lane == 31 ? bB : cB;
                 }
                 if (!lastS) {  // prefetch the boundary of lane 31's next row (uniform address)
                     const int ib = max(Ls - tp - 1, 0);
-                    pbM = BND_M(ib); pbD = BND_D(ib); pbE = BND_E(ib); pbG = BND_G(ib);
+                    pbv = BND_V(ib); pbG = BND_G(ib);
                 }
                 const int tF = Ls + 31 - tp;  // forward tile row holding row i of this lane (valid for i >= 1)
-                float FMv[C], FIv[C];
-#pragma unroll
-                for (int c = 0; c < C; c++) { FMv[c] = FMn[c]; FIv[c] = FIn[c]; }
-                const int toffc = toff;
-                if (tp + 1 < nstepsB) {   // prefetch the forward row of the next step (tile row 0 exists and is never used)
-                    toff -= 32 * C;
-                    const float *fmn = tM + toff, *fin = tI + toff;
-                    if (C % 4 == 0) {
-#pragma unroll
-                        for (int v = 0; v < C / 4; v++) {
-                            float4 a = reinterpret_cast<const float4 *>(fmn)[v];
-                            FMn[4 * v] = a.x; FMn[4 * v + 1] = a.y; FMn[4 * v + 2] = a.z; FMn[4 * v + 3] = a.w;
-                            if (ALIGN) {
-                                float4 b = reinterpret_cast<const float4 *>(fin)[v];
-                                FIn[4 * v] = b.x; FIn[4 * v + 1] = b.y; FIn[4 * v + 2] = b.z; FIn[4 * v + 3] = b.w;
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < C; c++) { FMn[c] = fmn[c]; if (ALIGN) FIn[c] = fin[c]; }
-                    }
-                }
+                // keep the ring W_RING-1 steps ahead (tile row 0 exists and is never used), then wait for this step's rows
+                __syncwarp();  // every lane has consumed the stage that is refilled now (it was read one step ago)
+                if (tq_next < nstepsB) ring_issue();
+                mbar_wait(ring_bar + rd_stage * 8, rd_phase);
+                const unsigned rs = ring_sa + rd_stage * RSB;
+                if (rd_stage == W_RING - 1) { rd_stage = 0; rd_phase ^= 1u; } else rd_stage++;
                 const int xres = xcur;
-                xcur = RES_AT(min(max(i - 1, 0), Ls - 1));
+                xcur = RES_AT(ALL ? i - 1 : min(max(i - 1, 0), Ls - 1));
                 if (act) {
                     float mn[C], mnR;
-                    if (i < Ls) {
+                    if (ALL || i < Ls) {
                         const int xr = xres;
                         float e[C];
                         lds_emis<C>(ebase + xr * erow, e);
@@ -398,7 +481,7 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, ALIGN ? 2 : 3) wave_kernel(De
 #pragma unroll
                     for (int c = 0; c < C; c++) bs = fmaf(mn[c], pen[c], bs);
                     bp = bs;
-                    if (i >= 1) {
+                    if (ALL || i >= 1) {
                         float nM[C], nI[C], nD[C];
 #pragma unroll
                         for (int c = C - 1; c >= 0; c--) {
@@ -408,21 +491,25 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, ALIGN ? 2 : 3) wave_kernel(De
                             nM[c] = fmaf(m1, oMM[c], fmaf(sI[c], oMI[c], fmaf(dr, oMD[c], ebs)));
                             nI[c] = fmaf(m1, oIM[c], sI[c] * oII[c]);
                         }
-                        // posterior decoding against the stored forward row
-                        float *fm = tM + toffc, *fi = tI + toffc;
+                        // posterior decoding against the stored forward row (this step's ring stage is complete)
+                        float FMv[C], FIv[C];
+#pragma unroll
+                        for (int v = 0; v < C / 4; v++) {
+                            const float4 a = lds_f4v(rs + v * 512);
+                            FMv[4 * v] = a.x; FMv[4 * v + 1] = a.y; FMv[4 * v + 2] = a.z; FMv[4 * v + 3] = a.w;
+                            if (ALIGN) {
+                                const float4 b = lds_f4v(rs + 32 * C * 4 + v * 512);
+                                FIv[4 * v] = b.x; FIv[4 * v + 1] = b.y; FIv[4 * v + 2] = b.z; FIv[4 * v + 3] = b.w;
+                            } else { FIv[4 * v] = 0.f; FIv[4 * v + 1] = 0.f; FIv[4 * v + 2] = 0.f; FIv[4 * v + 3] = 0.f; }
+                        }
                         if (ALIGN) {
                             float pM[C], pI[C];
 #pragma unroll
                             for (int c = 0; c < C; c++) { pM[c] = FMv[c] * nM[c] * fac; pI[c] = FIv[c] * nI[c] * fac; }
-                            if (C % 4 == 0) {
 #pragma unroll
-                                for (int v = 0; v < C / 4; v++) {
-                                    reinterpret_cast<float4 *>(fm)[v] = make_float4(pM[4 * v], pM[4 * v + 1], pM[4 * v + 2], pM[4 * v + 3]);
-                                    reinterpret_cast<float4 *>(fi)[v] = make_float4(pI[4 * v], pI[4 * v + 1], pI[4 * v + 2], pI[4 * v + 3]);
-                                }
-                            } else {
-#pragma unroll
-                                for (int c = 0; c < C; c++) { fm[c] = pM[c]; fi[c] = pI[c]; }
+                            for (int v = 0; v < C / 4; v++) {
+                                *reinterpret_cast<float4 *>(tMw + 128 * v) = make_float4(pM[4 * v], pM[4 * v + 1], pM[4 * v + 2], pM[4 * v + 3]);
+                                *reinterpret_cast<float4 *>(tIw + 128 * v) = make_float4(pI[4 * v], pI[4 * v + 1], pI[4 * v + 2], pI[4 * v + 3]);
                             }
                         } else {
 #pragma unroll
@@ -434,7 +521,7 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, ALIGN ? 2 : 3) wave_kernel(De
                     rMb = cMb;
                     ebs *= ploop;
                     if (lane == 0) {
-                        if (!firstS) { BND_M(i) = sM[0]; BND_D(i) = sD[0]; BND_E(i) = bp; BND_G(i) = g; }
+                        if (!firstS) { BND_V(i) = make_float4(sM[0], 0.f, sD[0], bp); BND_G(i) = g; }
                         else {
                             // N_b(i) = N_b(i+1)*loop + B_b(i)*move   (N_b(Ls) = 0)
                             const float f = pow2i(xNg - g);
@@ -444,11 +531,16 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, ALIGN ? 2 : 3) wave_kernel(De
                         }
                     }
                 }
+                if (ALIGN) { tMw -= 32 * C; tIw -= 32 * C; }
                 if (((tF - 1) & 7) == 0 && tF > 1) {  // next step enters the previous exponent block
-                    gFc = gFs[(tF - 2) >> 3];
+                    gFc = gFnext;
+                    gblk--;
+                    gFnext = gFs[max(gblk - 1, 0)];
                     fac = exp2f((float)(gFc + g - gT)) * invT;
                 }
-                if ((tp & (W_SCALE_EVERY - 1)) == (W_SCALE_EVERY - 1)) {
+            };
+            auto brescale = [&](const int tp) {
+                {
                     float mx = 0.f;
 #pragma unroll
                     for (int c = 0; c < C; c++) mx = fmaxf(mx, fmaxf(sM[c], fmaxf(sI[c], sD[c])));
@@ -459,8 +551,9 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, ALIGN ? 2 : 3) wave_kernel(De
                     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
                     int e_need = (mx > 1048576.f) ? fexp(mx) : 0;
                     if (!lastS) {
-                        int ahead = BND_G(max(0, Ls - (tp + W_SCALE_EVERY))) - 40 - g;
+                        const int ahead = aheadG - 40 - g;
                         e_need = max(e_need, ahead);
+                        aheadG = BND_G(max(0, Ls - (tp + 2 * W_SCALE_EVERY)));
                     }
                     if (e_need > 0) {
                         const float f = pow2i(-e_need);
@@ -470,6 +563,24 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, ALIGN ? 2 : 3) wave_kernel(De
                         rMb *= f; bp *= f; ebs *= f;
                         fac = exp2f((float)(gFc + g - gT)) * invT;
                     }
+                }
+            };
+            {
+                const std::integral_constant<bool, false> genc;
+                const std::integral_constant<bool, true> allc;
+                int tp = 0;
+                for (; tp < 32; tp++) {   // ramp-up (nstepsB = Ls + 32 >= 33)
+                    bstep(tp, genc);
+                    if ((tp & (W_SCALE_EVERY - 1)) == (W_SCALE_EVERY - 1)) brescale(tp);
+                }
+                for (; tp + 7 <= Ls - 1; tp += 8) {   // steady state: every lane has 1 <= i < Ls; blocks of 8 steps
+#pragma unroll 1
+                    for (int u = 0; u < 8; u++) bstep(tp + u, allc);
+                    brescale(tp + 7);
+                }
+                for (; tp < nstepsB; tp++) {   // drain
+                    bstep(tp, genc);
+                    if ((tp & (W_SCALE_EVERY - 1)) == (W_SCALE_EVERY - 1)) brescale(tp);
                 }
             }
             if (!ALIGN) {
@@ -610,10 +721,14 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, ALIGN ? 2 : 3) wave_kernel(De
                     }
                     if (act) {
                         const float xB = rNOA[i - 1];
-                        const float *fm = tM + ((size_t)t * 32 + lane) * C, *fi = tI + ((size_t)t * 32 + lane) * C;
+                        const float *fm = tM + (size_t)t * 32 * C + lane * 4, *fi = tI + (size_t)t * 32 * C + lane * 4;
                         float pM[C], pI[C];
 #pragma unroll
-                        for (int c = 0; c < C; c++) { pM[c] = fm[c]; pI[c] = fi[c]; }
+                        for (int v = 0; v < C / 4; v++) {
+                            const float4 a = *reinterpret_cast<const float4 *>(fm + 128 * v), b = *reinterpret_cast<const float4 *>(fi + 128 * v);
+                            pM[4 * v] = a.x; pM[4 * v + 1] = a.y; pM[4 * v + 2] = a.z; pM[4 * v + 3] = a.w;
+                            pI[4 * v] = b.x; pI[4 * v + 1] = b.y; pI[4 * v + 2] = b.z; pI[4 * v + 3] = b.w;
+                        }
                         float nM[C], nI[C], nD[C];
                         unsigned word = 0;
 #pragma unroll
