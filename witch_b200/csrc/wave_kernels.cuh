@@ -69,6 +69,9 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" :: "r"(bar), "r"(parity) : "memory");
 }
+__device__ __forceinline__ int lds_i1v(unsigned a) { int v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+constexpr int W_BND_SLOTS = 3;      // ring of 8-row blocks of strip-boundary records (256 B each) per warp
+__host__ __device__ constexpr int wave_bnd_ring_bytes() { return W_BND_SLOTS * (256 + 8); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ float4 lds_f4v(unsigned a) {
     float4 v;
@@ -89,7 +92,7 @@ __host__ __device__ inline WaveLayout wave_layout(int Lcap, int max_strips, int 
     w.tileM = o; o += tile;
     w.tileI = o; if (align) o += tile;  // insert rows are kept for the align stage only
     w.gF = o; o += ((long long)max_strips * (w.TT / 8 + 2) * 4 + 15) / 16 * 16;  // one exponent per 8 steps
-    w.bnd = o; o += (long long)8 * (Lcap + 2) * 4;    // boundary records {M,I,D,E,G,-,-,-} per row
+    w.bnd = o; o += (long long)8 * (Lcap + 16) * 4;   // boundary records {M,I,D,E,G,-,-,-} per row (read in blocks of 8 rows)
     w.rows = o; o += (long long)10 * (Lcap + 2) * 4;  // FC,FCg,NB,NBg,NOA,PPC,EOA,KE,...
     w.bits = o; if (align) o += (long long)max_strips * w.TT * 32 * 4;
     w.total = (o + 255) / 256 * 256;
@@ -156,16 +159,37 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, 
     // ring state persists across strips and items (the mbarriers are initialised once; phases keep alternating)
     int rd_stage = 0, wr_stage = 0;
     unsigned rd_phase = 0;
-    if (RING) {
-        constexpr int RSB0 = wave_ring_stage_bytes(C, ALIGN);
-        const unsigned bar0 = emis_sa + Wk.emis_floats * 4 + WAVE_WARPS * Wk.res_cap + WAVE_WARPS * (W_RING * RSB0) + w * (W_RING * 8);
-        if (lane == 0) {
+    int bq_w = 0, bq_r = 0;   // boundary-record ring: next slot to fill / to wait for
+    unsigned bq_ph = 0;
+    // dynamic shared memory after the emission table: residues | Forward-row ring | its mbarriers | boundary ring | its mbarriers
+    constexpr int RSB = wave_ring_stage_bytes(C, ALIGN);
+    const unsigned sm_dyn = emis_sa + Wk.emis_floats * 4;
+    const unsigned ring_w = sm_dyn + WAVE_WARPS * Wk.res_cap + w * (W_RING * RSB);
+    const unsigned ring_sa = ring_w + lane * 16;
+    const unsigned ring_bar = sm_dyn + WAVE_WARPS * Wk.res_cap + WAVE_WARPS * (W_RING * RSB) + w * (W_RING * 8);
+    const unsigned bnd_ring = sm_dyn + WAVE_WARPS * Wk.res_cap + WAVE_WARPS * (W_RING * (RSB + 8)) + w * (W_BND_SLOTS * 256);
+    const unsigned bnd_bar = sm_dyn + WAVE_WARPS * Wk.res_cap + WAVE_WARPS * (W_RING * (RSB + 8) + W_BND_SLOTS * 256) + w * (W_BND_SLOTS * 8);
+    if (lane == 0) {
 #pragma unroll
-            for (int k = 0; k < W_RING; k++) mbar_init(bar0 + k * 8, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncwarp();
+        for (int k = 0; k < W_RING; k++) mbar_init(ring_bar + k * 8, 1);
+#pragma unroll
+        for (int k = 0; k < W_BND_SLOTS; k++) mbar_init(bnd_bar + k * 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    __syncwarp();
+    // boundary records of the neighbouring strip arrive in blocks of 8 rows through a small TMA-fed ring
+    auto bnd_issue = [&](const int b) {
+        if (lane == 0) {
+            mbar_expect_tx(bnd_bar + bq_w * 8, 256);
+            tma_load_1d(bnd_ring + bq_w * 256, bnd + 64 * b, 256, bnd_bar + bq_w * 8);
+        }
+        bq_w = (bq_w == W_BND_SLOTS - 1) ? 0 : bq_w + 1;
+    };
+    auto bnd_wait = [&]() {
+        mbar_wait(bnd_bar + bq_r * 8, bq_ph);
+        if (bq_r == W_BND_SLOTS - 1) { bq_r = 0; bq_ph ^= 1u; } else bq_r++;
+    };
+    auto bnd_next = [](const int sl) { return sl == W_BND_SLOTS - 1 ? 0 : sl + 1; };
     int loaded_h = -1, Mstr = 0;
     for (;;) {
         __syncthreads();
@@ -202,11 +226,7 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, 
             __syncwarp();
         }
 #define RES_AT(idx) lds_u8(sresp + (idx))
-        // this warp's ring of stored Forward rows: [stage][M|I][v][lane][4 floats]  (conflict-free LDS.128)
-        constexpr int RSB = wave_ring_stage_bytes(C, ALIGN);
-        const unsigned ring_w = emis_sa + Wk.emis_floats * 4 + WAVE_WARPS * Wk.res_cap + w * (W_RING * RSB);
-        const unsigned ring_sa = ring_w + lane * 16;
-        const unsigned ring_bar = emis_sa + Wk.emis_floats * 4 + WAVE_WARPS * Wk.res_cap + WAVE_WARPS * (W_RING * RSB) + w * (W_RING * 8);
+        // (this warp's ring of stored Forward rows: [stage][M|I][v][lane][4 floats], conflict-free LDS.128)
         const long long po = E.poff[h];
         const float pmove = 2.0f / ((float)Lfull + 2.0f), ploop = 1.0f - pmove;
         const unsigned FULL = 0xffffffffu;
@@ -243,10 +263,18 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, 
             if (ALIGN) PIN64(tI);
             if (last) { xCv = 0.f; xCg = g; }
             int xcur = RES_AT(min(max(-lane, 0), Ls - 1));  // residue of the lane's row at the next step
-            float4 pbv = make_float4(0.f, 0.f, 0.f, 0.f);  // strip boundary {M,I,D,E} of lane 0's next row (prefetched)
-            int pbG = 0;
-            if (s > 0) { pbv = BND_V(1); pbG = BND_G(1); }
-            int aheadG = (s > 0) ? BND_G(min(Ls, 2 * W_SCALE_EVERY)) : 0;  // exponent the left strip had one block ahead (prefetched)
+            int bcur = 0;  // ring slot of the boundary block that holds lane 0's current row
+            if (s > 0) {
+                fence_proxy_async();  // the left strip's records (generic-proxy stores of this warp) before the TMA reads
+                __syncwarp();
+                bcur = bq_r;
+                const int bmax = Ls >> 3;
+                bnd_issue(0);
+                if (bmax >= 1) bnd_issue(1);
+                if (bmax >= 2) bnd_issue(2);
+                bnd_wait();
+                if (bmax >= 1) bnd_wait();
+            }
             float *tMp = tM + toff, *tIp = tI + toff;  // running tile pointers of the current step
             // One wavefront step. ALL = every lane is inside the sequence (steady state: no activity predicate, no clamps).
             auto fstep = [&](const int t, auto allc) {
@@ -260,13 +288,22 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, 
                 float cE = __shfl_up_sync(FULL, ep, 1);
                 {   // lane 0: strip boundary of the left strip, or zeros (first strip / outside the sequence); branch-free
                     float f = 0.f;
-                    if (s > 0) f = act ? pow2i(pbG - g) : 0.f;
+                    float4 pbv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (s > 0) {
+                        const int tr = ALL ? t : min(t, Ls);
+                        if ((t & 7) == 0 && (ALL || t <= Ls)) {   // row t opens boundary block t >> 3
+                            const int b = t >> 3;
+                            __syncwarp();  // the slot refilled now was last read a block ago
+                            if (8 * (b + 2) <= Ls) bnd_issue(b + 2);
+                            if (8 * (b + 1) <= Ls) bnd_wait();   // keep the next block readable too (exponent look-ahead)
+                            bcur = bnd_next(bcur);
+                        }
+                        const unsigned ra = bnd_ring + bcur * 256 + (tr & 7) * 32;
+                        pbv = lds_f4v(ra);
+                        f = act ? pow2i(lds_i1v(ra + 16) - g) : 0.f;
+                    }
                     const float bM = pbv.x * f, bI = pbv.y * f, bD = pbv.z * f, bE = pbv.w * f;
                     cM = lane == 0 ? bM : cM; cI = lane == 0 ? bI : cI; cD = lane == 0 ? bD : cD; cE = lane == 0 ? bE : cE;
-                }
-                if (s > 0) {  // prefetch the boundary of row t+1 (uniform address, consumed by lane 0 next step)
-                    const int ib = min(t + 1, Ls);
-                    pbv = BND_V(ib); pbG = BND_G(ib);
                 }
                 const int xres = xcur;
                 xcur = RES_AT(ALL ? i : min(max(i, 0), Ls - 1));
@@ -324,10 +361,11 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, 
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
                     int e_need = (mx > 1048576.f) ? fexp(mx) : 0;
-                    if (s > 0) {
-                        const int ahead = aheadG - 40 - g;
+                    if (s > 0) {   // exponent the left strip had 8 rows ahead (that block is already in the ring)
+                        const int r = min(Ls, t + W_SCALE_EVERY), tc = min(t, Ls);
+                        const int sl = ((r >> 3) == (tc >> 3)) ? bcur : bnd_next(bcur);
+                        const int ahead = lds_i1v(bnd_ring + sl * 256 + (r & 7) * 32 + 16) - 40 - g;
                         e_need = max(e_need, ahead);
-                        aheadG = BND_G(min(Ls, t + 2 * W_SCALE_EVERY));
                     }
                     if (e_need > 0) {
                         const float f = pow2i(-e_need);
@@ -404,10 +442,7 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, 
             if (ALIGN) PIN64(tI);
             if (firstS) { xNv = 0.f; xNg = g; }
             int xcur = RES_AT(Ls - 1);  // residue i+1 of the lane's row at the next step
-            float4 pbv = make_float4(0.f, 0.f, 0.f, 0.f);  // strip boundary {M,-,D,B} of lane 31's next row (prefetched)
-            int pbG = 0;
-            if (!lastS) { pbv = BND_V(Ls); pbG = BND_G(Ls); }
-            int aheadG = lastS ? 0 : BND_G(max(0, Ls - (2 * W_SCALE_EVERY - 1)));  // right strip's exponent one block ahead
+            int bcur = 0;  // ring slot of the boundary block that holds lane 31's current row
             int gblk = (Ls + 30) >> 3;
             int gFc = gFs[gblk];
             int gFnext = gFs[max(gblk - 1, 0)];      // exponent of the next (earlier) block of forward steps, prefetched
@@ -431,10 +466,19 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, 
                 wr_stage = (wr_stage == W_RING - 1) ? 0 : wr_stage + 1;
                 tq_next++;
             };
-            fence_proxy_async();  // this warp's generic-proxy writes of the tile are ordered before the TMA reads
+            fence_proxy_async();  // this warp's generic-proxy writes (tile, boundary records) are ordered before the TMA reads
             __syncwarp();
 #pragma unroll
             for (int k = 0; k < W_RING - 1; k++) ring_issue();   // nstepsB >= 32 > W_RING
+            if (!lastS) {
+                bcur = bq_r;
+                const int b0 = Ls >> 3;
+                bnd_issue(b0);
+                if (b0 >= 1) bnd_issue(b0 - 1);
+                if (b0 >= 2) bnd_issue(b0 - 2);
+                bnd_wait();
+                if (b0 >= 1) bnd_wait();
+            }
 
             // One wavefront step. ALL = every lane has 1 <= i < Ls (steady state: no predicates, no clamps).
             auto bstep = [&](const int tp, auto allc) {
@@ -446,13 +490,22 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, 
                 float cB = __shfl_down_sync(FULL, bp, 1);
                 {   // lane 31: boundary of the strip to the right, or zeros (last strip / outside the sequence); branch-free
                     float f = 0.f;
-                    if (!lastS) f = act ? pow2i(pbG - g) : 0.f;
+                    float4 pbv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (!lastS) {
+                        const int i31 = ALL ? Ls - tp : max(Ls - tp, 0);   // lane 31's row
+                        if ((i31 & 7) == 7 && tp > 0 && (ALL || tp <= Ls)) {   // row i31 opens the next lower boundary block
+                            const int b = i31 >> 3;
+                            __syncwarp();
+                            if (b >= 2) bnd_issue(b - 2);
+                            if (b >= 1) bnd_wait();
+                            bcur = bnd_next(bcur);
+                        }
+                        const unsigned ra = bnd_ring + bcur * 256 + (i31 & 7) * 32;
+                        pbv = lds_f4v(ra);
+                        f = act ? pow2i(lds_i1v(ra + 16) - g) : 0.f;
+                    }
                     const float bM = pbv.x * f, bD = pbv.z * f, bB = pbv.w * f;
                     cMb = lane == 31 ? bM : cMb; cDb = lane == 31 ? bD : cDb; cB = lane == 31 ? bB : cB;
-                }
-                if (!lastS) {  // prefetch the boundary of lane 31's next row (uniform address)
-                    const int ib = max(Ls - tp - 1, 0);
-                    pbv = BND_V(ib); pbG = BND_G(ib);
                 }
                 const int tF = Ls + 31 - tp;  // forward tile row holding row i of this lane (valid for i >= 1)
                 // keep the ring W_RING-1 steps ahead (tile row 0 exists and is never used), then wait for this step's rows
@@ -550,10 +603,11 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, 
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
                     int e_need = (mx > 1048576.f) ? fexp(mx) : 0;
-                    if (!lastS) {
-                        const int ahead = aheadG - 40 - g;
+                    if (!lastS) {   // exponent the right strip had 8 rows ahead (that block is already in the ring)
+                        const int ic = max(Ls - tp, 0), r = max(0, Ls - (tp + W_SCALE_EVERY));
+                        const int sl = ((r >> 3) == (ic >> 3)) ? bcur : bnd_next(bcur);
+                        const int ahead = lds_i1v(bnd_ring + sl * 256 + (r & 7) * 32 + 16) - 40 - g;
                         e_need = max(e_need, ahead);
-                        aheadG = BND_G(max(0, Ls - (tp + 2 * W_SCALE_EVERY)));
                     }
                     if (e_need > 0) {
                         const float f = pow2i(-e_need);
