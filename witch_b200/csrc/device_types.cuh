@@ -14,6 +14,7 @@ constexpr float LOG2E_F = 1.4426950408889634f;
 // (index = node k, node 0 and nodes > M are all-zero) and a [Kp][stride[h]] block of `emis` at eoff[h].
 struct DevEhmm {
     const float *tMM, *tMI, *tMD, *tIM, *tII, *tDM, *tDD, *entry;
+    const float *gD;  // gD[k] = 1 + tDD[k]*gD[k+1] (Backward D-state response to a unit E exit; used by the parser)
     const float *emis;
     const int *M;
     const int *stride;

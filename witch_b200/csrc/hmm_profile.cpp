@@ -150,6 +150,8 @@ HostProfile load_profile(const std::string &path, int /*pad_to*/) {
         p.tII[k] = (float)tp[4]; p.tDM[k] = (float)tp[5]; p.tDD[k] = (float)tp[6];
     }
     for (int k = 1; k <= M; k++) p.entry[k] = (float)(occ[k] / Z);
+    p.gD.assign(stride, 1.0f);  // beyond the model tDD = 0, so the response stays 1 (padded columns never feed back)
+    for (int k = M; k >= 0; k--) p.gD[k] = 1.0f + p.tDD[k] * (k + 1 < stride ? p.gD[k + 1] : 0.0f);
     p.emis.assign((size_t)Kp * stride, 0.0f);
     std::vector<double> sc(Kp);
     for (int k = 1; k <= M; k++) {

@@ -29,6 +29,7 @@ struct HostProfile {
     // transitions out of node k (k = 1..M-1 non-zero; node 0 and node M are zero as in p7_ProfileConfig)
     std::vector<float> tMM, tMI, tMD, tIM, tII, tDM, tDD;
     std::vector<float> entry;            // B->M_k (occupancy-weighted local entry), k = 1..M
+    std::vector<float> gD;               // gD[k] = 1 + tDD[k]*gD[k+1]: Backward D_k response to a unit E exit (model constant)
     std::vector<float> emis;             // [Kp][stride] match odds ratios; insert odds == 1
     int stride = 0;                      // row stride of emis (= padded length)
 };

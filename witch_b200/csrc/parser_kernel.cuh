@@ -59,7 +59,8 @@ __device__ __forceinline__ void load_emis(const float *row, int T, int j, float 
     }
 }
 
-constexpr int S_RED = 32;  // max warps per CTA
+constexpr int S_RED = 32;  // words per row of the reduction area
+constexpr int PARSER_RED_ROWS = 13;
 
 // 32-bit shared-memory addressing helpers: keep hot-loop addresses as one pinned register + immediate offsets
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -86,22 +87,24 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser_kernel(DevEhmm E, DevQue
     PIN32(lane); PIN32(w); PIN32(NW);
     const int TC = T * C;
     float *emis_s = smem;                       // [nsym][TC]
-    float *s_tot = emis_s + (size_t)Q.nsym * TC;  // [32]
-    float *s_es = s_tot + S_RED;
-    float *s_pw = s_es + S_RED;
-    float *s_bM = s_pw + S_RED;  // [2][32]
-    float *s_bI = s_bM + 2 * S_RED;
-    (void)s_bI;
-    unsigned red_sa = smem_u32(s_tot);           // reduction area: tot, es, pw, bM[2], bI[2], bD[2] (32 words each)
+    float *s_tot = emis_s + (size_t)Q.nsym * TC;  // reduction area: PARSER_RED_ROWS rows of 32 words
+    unsigned red_sa = smem_u32(s_tot);
     unsigned emis_ta = smem_u32(emis_s) + tid * 16;  // this thread's slot in an emission row (interleaved layout)
     unsigned erow_b = TC * 4, estep = T * 16;
     PIN32(red_sa); PIN32(emis_ta); PIN32(erow_b); PIN32(estep);
-#define SA_TOT(x) (red_sa + 4 * (x))
-#define SA_ES(x) (red_sa + 128 + 4 * (x))
-#define SA_PW(x) (red_sa + 256 + 4 * (x))
-#define SA_BM(par, x) (red_sa + 384 + 128 * (par) + 4 * (x))
-#define SA_BI(par, x) (red_sa + 640 + 128 * (par) + 4 * (x))
-#define SA_BD(par, x) (red_sa + 896 + 128 * (par) + 4 * (x))
+    // reduction area (32-word rows): TOT[2], ES[2], BM[2], BI[2], BV[2] double-buffered by row parity; PW, KW, AC constants
+#define SA_TOT2(par, x) (red_sa + (par) + 4 * (x))
+#define SA_ES2(par, x) (red_sa + 256 + (par) + 4 * (x))
+#define SA_BM2(par, x) (red_sa + 512 + (par) + 4 * (x))
+#define SA_BI2(par, x) (red_sa + 768 + (par) + 4 * (x))
+#define SA_BV2(par, x) (red_sa + 1024 + (par) + 4 * (x))
+#define SA_PW(x) (red_sa + 1280 + 4 * (x))
+#define SA_KW(x) (red_sa + 1408 + 4 * (x))
+#define SA_AC(x) (red_sa + 1536 + 4 * (x))
+    // (Backward pass names for the same rows)
+#define SA_TOT(x) SA_TOT2(0, x)
+#define SA_ES(x) SA_ES2(0, x)
+#define SA_BM(par, x) SA_BM2((par) * 128, x)
     __shared__ int s_item;
 
     const int Lr = (Wk.Lcap + 4) & ~3;                         // rows, rounded so that every array stays 16-byte aligned
@@ -114,6 +117,7 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser_kernel(DevEhmm E, DevQue
     float *dBT = dMO + Lr;                                     // btot prefix
     float *dET = dBT + Lr;                                     // etot prefix
 
+    for (int z = tid; z < PARSER_RED_ROWS * S_RED; z += T) s_tot[z] = 0.f;  // slots of warps >= NW stay zero
     const long long nitems = (long long)Wk.nh * Wk.nq;
     int loaded_h = -1;
     for (;;) {
@@ -150,6 +154,13 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser_kernel(DevEhmm E, DevQue
         const float EC = 0.5f, EJ = 0.5f;
 
         // =========================== Forward ===========================
+        // One barrier per row. Everything a row needs from the other threads is linear in per-thread quantities
+        // that are known before the barrier, so the three CTA-wide combinations run side by side after it:
+        //   Z_w    = D entering this warp's first column          = sum_l tot[l] * cz[l]
+        //   Z_{w-1} (for the D value the left warp's last column hands to lane 0 of this warp)
+        //   E(i)   = sum_t [a_t + SP_t * X_t] = sum_w es[w] + sum_l tot[l] * KK[l]
+        // with a_t = sum_c (M + local D), SP_t = sum_c pDD[c], X_t the D value entering the thread. All the weights
+        // (cz, cz2, KK, R, K_w, A_w) are products/sums of tDD over columns: constants of the (HMM, thread).
         float pa[C], pb[C], pg[C], pmd[C], pdd[C], pmi[C], pii[C], pen[C], pDD[C];
         load_cols<C>(E.tMM + po, k0, pa);   // into column k0+1+cc from node k0+cc
         load_cols<C>(E.tIM + po, k0, pb);
@@ -163,9 +174,14 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser_kernel(DevEhmm E, DevQue
         pDD[0] = 1.f;
 #pragma unroll
         for (int c = 1; c < C; c++) pDD[c] = pDD[c - 1] * pdd[c];
-        float coef[5], Cexcl;
+        float coef[5], Cexcl, Rt, KKl, czl, czl2, Aprev;
+        const int lw = lane & 15;   // cross-warp combinations: both half-warps mirror warps 0..15 (NW <= 16)
         {
-            float Pc = pDD[C - 1] * ddo;
+            float SP = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; c++) SP += pDD[c];
+            const float Pt = pDD[C - 1] * ddo;
+            float Pc = Pt;
 #pragma unroll
             for (int s = 0; s < 5; s++) {
                 float up = __shfl_up_sync(0xffffffffu, Pc, 1 << s);
@@ -174,45 +190,79 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser_kernel(DevEhmm E, DevQue
             }
             Cexcl = __shfl_up_sync(0xffffffffu, Pc, 1);
             if (lane == 0) Cexcl = 1.f;
-            if (lane == 31) sts_f1(SA_PW(w), Pc);
+            // R_l = sum_{l' > l} SP_l' * prod_{l < l'' < l'} P_l''   (weight of this thread's local chain output in E)
+            Rt = 0.f;
+            for (int it = 0; it < 31; it++) {
+                const float dn = __shfl_down_sync(0xffffffffu, fmaf(Pt, Rt, SP), 1);
+                Rt = (lane < 31) ? dn : 0.f;
+            }
+            float kw = SP * Cexcl;   // K_w = sum_l SP_l * Cexcl_l
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) kw += __shfl_xor_sync(0xffffffffu, kw, o);
+            if (lane == 31) { sts_f1(SA_PW(w), Pc); sts_f1(SA_AC(w), pDD[C - 1] * Cexcl); }
+            if (lane == 0) sts_f1(SA_KW(w), kw);
         }
         __syncthreads();
-        // lane l of warp w keeps cz = prod_{l < w'' < w} PW[w'']  (0 for l >= w): Z_w = sum_l tot[l] * cz
-        float czl = 0.f;
-        if (lane < w) {
-            czl = 1.f;
-            for (int ww = lane + 1; ww < w; ww++) czl *= lds_f1v(SA_PW(ww));
+        {
+            // lane lw stands for warp lw: cz = prod_{lw < w'' < w} PW[w''] (0 for lw >= w), cz2 the same for w-1,
+            // KK = sum_{w2 > lw} K[w2] * prod_{lw < w'' < w2} PW[w'']
+            czl = 0.f; czl2 = 0.f; KKl = 0.f;
+            if (lw < w) { czl = 1.f; for (int ww = lw + 1; ww < w; ww++) czl *= lds_f1v(SA_PW(ww)); }
+            if (lw < w - 1) { czl2 = 1.f; for (int ww = lw + 1; ww < w - 1; ww++) czl2 *= lds_f1v(SA_PW(ww)); }
+            if (lw < NW) {
+                float pr = 1.f;
+                for (int w2 = lw + 1; w2 < NW; w2++) { KKl = fmaf(lds_f1v(SA_KW(w2)), pr, KKl); pr *= lds_f1v(SA_PW(w2)); }
+            }
+            Aprev = (w > 0) ? lds_f1v(SA_AC(w - 1)) : 0.f;
         }
-        float sM[C], sI[C], sD[C];
+        float sM[C], sI[C], sD[C], dl[C];
 #pragma unroll
-        for (int c = 0; c < C; c++) { sM[c] = 0.f; sI[c] = 0.f; sD[c] = 0.f; }
-        float xN = 1.f, xB = pmove, xE = 0.f, xJ = 0.f, xC = 0.f;
+        for (int c = 0; c < C; c++) { sM[c] = 0.f; sI[c] = 0.f; sD[c] = 0.f; dl[c] = 0.f; }
+        float xN = 1.f, xB = pmove, xE = 0.f, xJ = 0.f, xC = 0.f, yex = 0.f, dL = 0.f;
         int sF = 0;
         if (tid == 0) { Fs[0] = xN; Fs[1] = xB; Fs[2] = 0.f; Fs[3] = 0.f; Fs[4] = 0.f; Fs[5] = 0.f; }
         __syncthreads();  // emis_s ready
         int xres = qd[0];
         float4 *fsrow = reinterpret_cast<float4 *>(Fs + 8);  // row i-1 is written while row i is computed
         PIN64(fsrow);
+        // finish row r (after its barrier): D column values, E(r) and the special states; returns the rescale factor
+        auto finish_row = [&](const int r) -> float {
+            const unsigned par = (r & 1) * 128;
+            const float tv = lds_f1v(SA_TOT2(par, lw)), ev = lds_f1v(SA_ES2(par, lw));
+            float z = tv * czl, z2 = tv * czl2, et = fmaf(tv, KKl, ev);   // (slots >= NW hold zeros)
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                z += __shfl_xor_sync(0xffffffffu, z, o);
+                z2 += __shfl_xor_sync(0xffffffffu, z2, o);
+                et += __shfl_xor_sync(0xffffffffu, et, o);
+            }
+            const float X = fmaf(Cexcl, z, yex);
+#pragma unroll
+            for (int c = 0; c < C; c++) sD[c] = fmaf(pDD[c], X, dl[c]);
+            dL = __shfl_up_sync(0xffffffffu, sD[C - 1], 1);
+            if (lane == 0) dL = (w > 0) ? fmaf(Aprev, z2, lds_f1v(SA_BV2(par, w - 1))) : 0.f;
+            const float Et = et;
+            xE = Et; xJ = xJ * ploop + Et * EJ; xC = xC * ploop + Et * EC; xN *= ploop; xB = (xN + xJ) * pmove;
+            float scl = 1.f;
+            if (Et > 1.0e12f) {
+                int e = fexp(Et);
+                scl = pow2i(-e); sF += e;
+                xE *= scl; xJ *= scl; xC *= scl; xN *= scl; xB *= scl; dL *= scl;
+#pragma unroll
+                for (int c = 0; c < C; c++) { sM[c] *= scl; sI[c] *= scl; sD[c] *= scl; }
+            }
+            return scl;
+        };
         for (int i = 1; i <= L; i++) {
             float scl = 1.f;
-            if (i > 1) {  // post(i-1)
-                float Et = (lane < NW) ? lds_f1v(SA_ES(lane)) : 0.f;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) Et += __shfl_xor_sync(0xffffffffu, Et, o);
-                xE = Et; xJ = xJ * ploop + Et * EJ; xC = xC * ploop + Et * EC; xN *= ploop; xB = (xN + xJ) * pmove;
-                if (Et > 1.0e12f) {
-                    int e = fexp(Et);
-                    scl = pow2i(-e); sF += e;
-                    xE *= scl; xJ *= scl; xC *= scl; xN *= scl; xB *= scl;
-#pragma unroll
-                    for (int c = 0; c < C; c++) { sM[c] *= scl; sI[c] *= scl; sD[c] *= scl; }
-                }
+            if (i > 1) {
+                scl = finish_row(i - 1);
                 if (tid == 0) {
                     fsrow[0] = make_float4(xN, xB, xE, xJ); fsrow[1] = make_float4(xC, (float)sF, 0.f, 0.f);
                 }
                 fsrow += 2;
             }
-            // pre(i)
+            // row i
             float e[C];
             {
                 const unsigned ea = emis_ta + xres * erow_b;
@@ -225,12 +275,11 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser_kernel(DevEhmm E, DevQue
             if (i < L) xres = qd[i];
             float mL = __shfl_up_sync(0xffffffffu, sM[C - 1], 1);
             float iL = __shfl_up_sync(0xffffffffu, sI[C - 1], 1);
-            float dL = __shfl_up_sync(0xffffffffu, sD[C - 1], 1);
             if (lane == 0) {
                 if (w > 0 && i > 1) {
-                    const int par = (i - 1) & 1;
-                    mL = lds_f1v(SA_BM(par, w - 1)) * scl; iL = lds_f1v(SA_BI(par, w - 1)) * scl; dL = lds_f1v(SA_BD(par, w - 1)) * scl;
-                } else { mL = 0.f; iL = 0.f; dL = 0.f; }
+                    const unsigned par = ((i - 1) & 1) * 128;
+                    mL = lds_f1v(SA_BM2(par, w - 1)) * scl; iL = lds_f1v(SA_BI2(par, w - 1)) * scl;
+                } else { mL = 0.f; iL = 0.f; }
             }
             float nM[C], nI[C];
 #pragma unroll
@@ -241,51 +290,38 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser_kernel(DevEhmm E, DevQue
                 acc = fmaf(pm, pa[c], acc); acc = fmaf(pi, pb[c], acc); acc = fmaf(pd, pg[c], acc);
                 nM[c] = acc * e[c];
             }
-            float dl[C];
             dl[0] = 0.f;
 #pragma unroll
             for (int c = 1; c < C; c++) dl[c] = fmaf(nM[c - 1], pmd[c], dl[c - 1] * pdd[c]);
-            float y = fmaf(nM[C - 1], mdo, dl[C - 1] * ddo);
+            const float yl = fmaf(nM[C - 1], mdo, dl[C - 1] * ddo);   // local output of the thread's D chain
+            float at = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; c++) { sM[c] = nM[c]; sI[c] = nI[c]; at += nM[c] + dl[c]; }
+            float y = yl, v = fmaf(yl, Rt, at);
 #pragma unroll
             for (int s = 0; s < 5; s++) {
-                float up = __shfl_up_sync(0xffffffffu, y, 1 << s);
+                const float up = __shfl_up_sync(0xffffffffu, y, 1 << s);
+                v += __shfl_xor_sync(0xffffffffu, v, 1 << s);
                 y = fmaf(coef[s], up, y);
             }
-            float yex = __shfl_up_sync(0xffffffffu, y, 1);
+            yex = __shfl_up_sync(0xffffffffu, y, 1);
             if (lane == 0) yex = 0.f;
-            if (lane == 31) {
-                sts_f1(SA_TOT(w), y);
-                sts_f1(SA_BM(i & 1, w), nM[C - 1]);
-                sts_f1(SA_BI(i & 1, w), nI[C - 1]);
+            {
+                const unsigned par = (i & 1) * 128;
+                if (lane == 31) {
+                    sts_f1(SA_TOT2(par, w), y);
+                    sts_f1(SA_BM2(par, w), nM[C - 1]);
+                    sts_f1(SA_BI2(par, w), nI[C - 1]);
+                    sts_f1(SA_BV2(par, w), fmaf(pDD[C - 1], yex, dl[C - 1]));
+                }
+                if (lane == 0) sts_f1(SA_ES2(par, w), v);
             }
-            __syncthreads();
-            // mid(i)
-            float Z = (lane < NW) ? lds_f1v(SA_TOT(lane)) * czl : 0.f;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) Z += __shfl_xor_sync(0xffffffffu, Z, o);
-            const float X = fmaf(Cexcl, Z, yex);
-            float es = 0.f;
-#pragma unroll
-            for (int c = 0; c < C; c++) {
-                sD[c] = fmaf(pDD[c], X, dl[c]);
-                sM[c] = nM[c]; sI[c] = nI[c];
-                es += sM[c] + sD[c];
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) es += __shfl_xor_sync(0xffffffffu, es, o);
-            if (lane == 0) sts_f1(SA_ES(w), es);
-            if (lane == 31) sts_f1(SA_BD(i & 1, w), sD[C - 1]);
             __syncthreads();
         }
-        {  // post(L)
-            float Et = (lane < NW) ? lds_f1v(SA_ES(lane)) : 0.f;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) Et += __shfl_xor_sync(0xffffffffu, Et, o);
-            xE = Et; xJ = xJ * ploop + Et * EJ; xC = xC * ploop + Et * EC; xN *= ploop; xB = (xN + xJ) * pmove;
-            if (tid == 0) {
-                float4 *r = reinterpret_cast<float4 *>(Fs + 8 * L);
-                r[0] = make_float4(xN, xB, xE, xJ); r[1] = make_float4(xC, (float)sF, 0.f, 0.f);
-            }
+        finish_row(L);
+        if (tid == 0) {
+            float4 *r = reinterpret_cast<float4 *>(Fs + 8 * L);
+            r[0] = make_float4(xN, xB, xE, xJ); r[1] = make_float4(xC, (float)sF, 0.f, 0.f);
         }
         const float Tm = xC * pmove;  // total = Tm * 2^sF
         const int sT = sF;

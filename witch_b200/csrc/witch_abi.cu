@@ -80,7 +80,7 @@ struct witch_ehmm {
     int device = 0, H = 0, alph = 0, Kp = 0, num_sms = 148;
     std::vector<int> M, nseq, stride;
     std::vector<long long> poff, eoff;
-    DevBuf<float> tMM, tMI, tMD, tIM, tII, tDM, tDD, entry, emis;
+    DevBuf<float> tMM, tMI, tMD, tIM, tII, tDM, tDD, entry, gD, emis;
     DevBuf<int> dM, dstride, dnseq;
     DevBuf<long long> dpoff, deoff;
     // reusable workspaces
@@ -92,7 +92,7 @@ struct witch_ehmm {
     DevEhmm view() const {
         DevEhmm v;
         v.tMM = tMM.p; v.tMI = tMI.p; v.tMD = tMD.p; v.tIM = tIM.p; v.tII = tII.p; v.tDM = tDM.p; v.tDD = tDD.p;
-        v.entry = entry.p; v.emis = emis.p; v.M = dM.p; v.stride = dstride.p; v.poff = dpoff.p; v.eoff = deoff.p;
+        v.entry = entry.p; v.gD = gD.p; v.emis = emis.p; v.M = dM.p; v.stride = dstride.p; v.poff = dpoff.p; v.eoff = deoff.p;
         v.H = H; v.Kp = Kp;
         return v;
     }
@@ -171,6 +171,7 @@ extern "C" int witch_ehmm_create(int n_hmm, const char *const *paths, witch_ehmm
         e->tMD.upload(cat(&HostProfile::tMD)); e->tIM.upload(cat(&HostProfile::tIM));
         e->tII.upload(cat(&HostProfile::tII)); e->tDM.upload(cat(&HostProfile::tDM));
         e->tDD.upload(cat(&HostProfile::tDD)); e->entry.upload(cat(&HostProfile::entry));
+        e->gD.upload(cat(&HostProfile::gD));
         e->emis.upload(cat(&HostProfile::emis));
         e->dM.upload(e->M); e->dstride.upload(e->stride); e->dnseq.upload(e->nseq);
         e->dpoff.upload(e->poff); e->deoff.upload(e->eoff);
@@ -260,7 +261,7 @@ static std::vector<SClass> s_classes(const witch_ehmm *e, const std::vector<int>
 
 template <int C, int MAXT, int MINB>
 static void launch_parser(const witch_ehmm *e, const witch_queries *q, int T, ParserWork wk, cudaStream_t st, int maxgrid) {
-    const size_t smem = ((size_t)q->nsym * T * C + 9 * S_RED) * sizeof(float);
+    const size_t smem = ((size_t)q->nsym * T * C + PARSER_RED_ROWS * S_RED) * sizeof(float);
     if (smem > 200 * 1024) throw std::runtime_error("emission table does not fit shared memory (too many symbols x model length)");
     CUDA_TRY(cudaFuncSetAttribute(mh_parser_kernel<C, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
