@@ -5,7 +5,8 @@ import os
 import tempfile
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-SETS = ("dna_small", "dna_sub8", "dna_full", "amino_small")
+# amino_extreme (tests/golden/make_golden_extreme.py): W/C-rich hand-written profiles, scores of thousands of bits
+SETS = ("dna_small", "dna_sub8", "dna_full", "amino_small", "amino_extreme")
 
 
 def read_fasta(path):

@@ -5,7 +5,7 @@ static int wave_C_for(const witch_ehmm *) { return 8; }
 struct WaveBucket { int Lcap; std::vector<WaveItem> items; };
 
 // Launches the wavefront kernel over `items` (any order); outputs indexed by WaveItem::pair.
-template <bool ALIGN, int C, int WAVE_WARPS, int MINB, int RING>
+template <bool ALIGN, int C, int WAVE_WARPS, int MINB, int RING, bool LANE_EXP>
 static void run_wave_c(witch_ehmm *e, witch_queries *q, std::vector<WaveItem> items, float *d_envsc, float *d_domcorr,
                      int *d_cols, const long long *d_coloff, float *d_dbg_fwd, float *d_dbg_bwd, cudaStream_t st) {
     if (items.empty()) return;
@@ -44,14 +44,14 @@ static void run_wave_c(witch_ehmm *e, witch_queries *q, std::vector<WaveItem> it
             gfirst.push_back((int)i); gcount.push_back((int)(j - i));
             i = j;
         }
-        const WaveLayout lay = wave_layout(Lcap, max_strips, C, ALIGN);
+        const WaveLayout lay = wave_layout(Lcap, max_strips, C, ALIGN, LANE_EXP);
         const int emis_floats = q->nsym * max_strips * SW;
         const int res_cap = (Lcap + 1 + 15) / 16 * 16;
         const size_t smem = (size_t)emis_floats * sizeof(float) + (size_t)WAVE_WARPS * res_cap +
                             (size_t)WAVE_WARPS * RING * (wave_ring_stage_bytes(C, ALIGN) + 8) +
                             (size_t)WAVE_WARPS * wave_bnd_ring_bytes();
         if (smem > 220 * 1024) throw std::runtime_error("emission table + residue staging do not fit shared memory");
-        auto kern = wave_kernel<C, ALIGN, WAVE_WARPS, MINB, RING>;
+        auto kern = wave_kernel<C, ALIGN, WAVE_WARPS, MINB, RING, LANE_EXP>;
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 1;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WAVE_WARPS * 32, smem));
@@ -84,8 +84,9 @@ template <bool ALIGN>
 static void run_wave(witch_ehmm *e, witch_queries *q, std::vector<WaveItem> items, float *d_envsc, float *d_domcorr,
                      int *d_cols, const long long *d_coloff, float *d_dbg_fwd, float *d_dbg_bwd, cudaStream_t st) {
 #define WV_ARGS e, q, std::move(items), d_envsc, d_domcorr, d_cols, d_coloff, d_dbg_fwd, d_dbg_bwd, st
-    if (ALIGN) run_wave_c<true, 8, 4, 2, 3>(WV_ARGS);
-    else run_wave_c<false, 8, 4, 3, 3>(WV_ARGS);
+    const bool lane_exp = e->alph == ALPH_AMINO;  // per-lane scaling exponents (see wave_kernels.cuh)
+    if (ALIGN) { if (lane_exp) run_wave_c<true, 8, 4, 2, 3, true>(WV_ARGS); else run_wave_c<true, 8, 4, 2, 3, false>(WV_ARGS); }
+    else { if (lane_exp) run_wave_c<false, 8, 4, 3, 3, true>(WV_ARGS); else run_wave_c<false, 8, 4, 3, 3, false>(WV_ARGS); }
 #undef WV_ARGS
 }
 

@@ -84,14 +84,14 @@ struct WaveLayout {
     long long tileM, tileI, gF, bnd, rows, bits, total;
     int TT;
 };
-__host__ __device__ inline WaveLayout wave_layout(int Lcap, int max_strips, int C, bool align) {
+__host__ __device__ inline WaveLayout wave_layout(int Lcap, int max_strips, int C, bool align, bool lane_exp) {
     WaveLayout w;
     w.TT = Lcap + 32;
     long long tile = (long long)max_strips * w.TT * 32 * C * 4;
     long long o = 0;
     w.tileM = o; o += tile;
     w.tileI = o; if (align) o += tile;  // insert rows are kept for the align stage only
-    w.gF = o; o += ((long long)max_strips * (w.TT / 8 + 2) * 4 + 15) / 16 * 16;  // one exponent per 8 steps
+    w.gF = o; o += ((long long)max_strips * (w.TT / 8 + 2) * (lane_exp ? 32 : 1) * 4 + 15) / 16 * 16;  // exponents per block of 8 steps
     w.bnd = o; o += (long long)8 * (Lcap + 16) * 4;   // boundary records {M,I,D,E,G,-,-,-} per row (read in blocks of 8 rows)
     w.rows = o; o += (long long)10 * (Lcap + 2) * 4;  // FC,FCg,NB,NBg,NOA,PPC,EOA,KE,...
     w.bits = o; if (align) o += (long long)max_strips * w.TT * 32 * 4;
@@ -119,7 +119,7 @@ __device__ __forceinline__ bool oa_e_better(float v2, int d2, int o2, float v1, 
     return d2 == 0 ? (o2 > o1) : (o2 < o1);  // last M in visiting order, first D in visiting order
 }
 
-template <int C, bool ALIGN, int WAVE_WARPS, int MINB, int W_RING>
+template <int C, bool ALIGN, int WAVE_WARPS, int MINB, int W_RING, bool LANE_EXP>
 __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, DevQueries Q, WaveWork Wk) {
     extern __shared__ float smem[];
     static_assert(W_RING >= 2, "the Backward sweep reads stored Forward rows through the TMA ring");
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, 
     __shared__ int s_group;
     __shared__ float s_n2[WAVE_WARPS][MAX_SYM];
     float *emis_s = smem;  // [nsym][Mstr] in strip-interleaved layout
-    const WaveLayout lay = wave_layout(Wk.Lcap, Wk.max_strips, C, ALIGN);
+    const WaveLayout lay = wave_layout(Wk.Lcap, Wk.max_strips, C, ALIGN, LANE_EXP);
     __shared__ char *s_slot[WAVE_WARPS];
     if (lane == 0) s_slot[w] = Wk.scratch + ((long long)blockIdx.x * WAVE_WARPS + w) * Wk.slot_bytes;
     __syncwarp();
@@ -152,7 +152,9 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, 
     float *rNOA = (float *)(rNBg + LB), *rPPC = rNOA + LB, *rEOA = rPPC + LB;
     int *rKE = (int *)(rEOA + LB);
     unsigned *bits = (unsigned *)(slot + lay.bits);
-    const int TT = lay.TT, TG = lay.TT / 8 + 2;
+    const int TT = lay.TT, TG = (lay.TT / 8 + 2) * (LANE_EXP ? 32 : 1);
+    // exponent of a block of 8 Forward steps: one word per warp (uniform exponent) or per lane (LANE_EXP)
+#define GF_AT(blk) (LANE_EXP ? (blk) * 32 + lane : (blk))
     const unsigned emis_sa = smem_u32(emis_s);
     const int SW = 32 * C;  // strip width
 
@@ -248,7 +250,10 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, 
             for (int c = 0; c < C; c++) { sM[c] = 0.f; sI[c] = 0.f; sD[c] = 0.f; }
             float rM = 0.f, rI = 0.f, rD = 0.f;      // row i-1 at the column left of the owned block
             float ep = 0.f;                          // running E(i) partial of the lane's last row
-            int g = (s > 0) ? BND_G(1) : 0;           // warp exponent
+            // Scaling exponent. DNA: one per warp (32 rows of <= 2 bits each fit FP32's range). LANE_EXP (amino: a row of a
+            // conserved rare residue is worth > 6 bits): one per lane, changed only at the common 8-step checks and
+            // coupled so that a neighbour's exponent is at most 16 above (values entering a lane convert by <= 2^16).
+            int g = (s > 0) ? BND_G(1) : 0;
             float xBs = pmove * pow2i(-g);           // pmove * N(i-1) * 2^-g for the lane's next row
             const bool last = (s == nstrips - 1);
             unsigned ebase = emis_sa + (s * SW + lane * 4) * 4;
@@ -286,6 +291,10 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, 
                 float cI = __shfl_up_sync(FULL, sI[C - 1], 1);
                 float cD = __shfl_up_sync(FULL, sD[C - 1], 1);
                 float cE = __shfl_up_sync(FULL, ep, 1);
+                if (LANE_EXP) {   // the left lane's values are in its own scale
+                    const float fl = pow2i(__shfl_up_sync(FULL, g, 1) - g);
+                    cM *= fl; cI *= fl; cD *= fl; cE *= fl;
+                }
                 {   // lane 0: strip boundary of the left strip, or zeros (first strip / outside the sequence); branch-free
                     float f = 0.f;
                     float4 pbv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -351,21 +360,32 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, 
                 if (ALIGN) tIp += 32 * C;
             };
             // every 8 steps: record the exponent of the block (for the Backward pass) / renormalise
-            auto fmark = [&](const int t) { if (lane == 0) gFs[(t - 1) >> 3] = g; };  // exponent of steps t .. t+7
+            auto fmark = [&](const int t) { if (LANE_EXP || lane == 0) gFs[GF_AT((t - 1) >> 3)] = g; };  // exponent of steps t .. t+7
             auto frescale = [&](const int t) {
                 {
                     float mx = 0.f;
 #pragma unroll
                     for (int c = 0; c < C; c++) mx = fmaxf(mx, fmaxf(sM[c], fmaxf(sI[c], sD[c])));
                     mx = fmaxf(mx, ep);
+                    if (!LANE_EXP) {
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
+                        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
+                    }
                     int e_need = (mx > 1048576.f) ? fexp(mx) : 0;
                     if (s > 0) {   // exponent the left strip had 8 rows ahead (that block is already in the ring)
                         const int r = min(Ls, t + W_SCALE_EVERY), tc = min(t, Ls);
                         const int sl = ((r >> 3) == (tc >> 3)) ? bcur : bnd_next(bcur);
                         const int ahead = lds_i1v(bnd_ring + sl * 256 + (r & 7) * 32 + 16) - 40 - g;
-                        e_need = max(e_need, ahead);
+                        if (!LANE_EXP || lane == 0) e_need = max(e_need, ahead);
+                    }
+                    if (LANE_EXP) {   // couple the lanes: g_l >= g_{l-1} - 16 (max-plus scan over the new exponents)
+                        int need = g + e_need;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int up = __shfl_up_sync(FULL, need, o);
+                            if (lane >= o) need = max(need, up - 16 * o);
+                        }
+                        e_need = need - g;
                     }
                     if (e_need > 0) {
                         const float f = pow2i(-e_need);
@@ -444,9 +464,13 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, 
             int xcur = RES_AT(Ls - 1);  // residue i+1 of the lane's row at the next step
             int bcur = 0;  // ring slot of the boundary block that holds lane 31's current row
             int gblk = (Ls + 30) >> 3;
-            int gFc = gFs[gblk];
-            int gFnext = gFs[max(gblk - 1, 0)];      // exponent of the next (earlier) block of forward steps, prefetched
-            float fac = exp2f((float)(gFc + g - gT)) * invT;  // posterior scale; refreshed when an exponent changes
+            int gFc = gFs[GF_AT(gblk)];
+            int gFnext = gFs[GF_AT(max(gblk - 1, 0))];  // exponent of the next (earlier) block of forward steps, prefetched
+            auto post_scale = [&](const int gf, const int gb) {
+                const float x = (float)(gf + gb - gT);
+                return exp2f(LANE_EXP ? fminf(x, 120.f) : x) * invT;
+            };
+            float fac = post_scale(gFc, g);  // posterior scale; refreshed when an exponent changes
             // Stored Forward rows come back through a shared-memory ring filled by TMA bulk copies, W_RING-1 steps ahead
             // of their use (one lane issues one copy per step: the step's rows of all 32 lanes are one contiguous run;
             // completion is an mbarrier transaction count, so no register scoreboard is tied up by the prefetch).
@@ -488,6 +512,10 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, 
                 float cMb = __shfl_down_sync(FULL, sM[0], 1);   // Mb(i, right column)   (row i of the right lane)
                 float cDb = __shfl_down_sync(FULL, sD[0], 1);   // Db(i, right column)
                 float cB = __shfl_down_sync(FULL, bp, 1);
+                if (LANE_EXP) {   // the right lane's values are in its own scale
+                    const float fl = pow2i(__shfl_down_sync(FULL, g, 1) - g);
+                    cMb *= fl; cDb *= fl; cB *= fl;
+                }
                 {   // lane 31: boundary of the strip to the right, or zeros (last strip / outside the sequence); branch-free
                     float f = 0.f;
                     float4 pbv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -558,7 +586,7 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, 
                         if (ALIGN) {
                             float pM[C], pI[C];
 #pragma unroll
-                            for (int c = 0; c < C; c++) { pM[c] = FMv[c] * nM[c] * fac; pI[c] = FIv[c] * nI[c] * fac; }
+                            for (int c = 0; c < C; c++) { pM[c] = (FMv[c] * fac) * nM[c]; pI[c] = (FIv[c] * fac) * nI[c]; }
 #pragma unroll
                             for (int v = 0; v < C / 4; v++) {
                                 *reinterpret_cast<float4 *>(tMw + 128 * v) = make_float4(pM[4 * v], pM[4 * v + 1], pM[4 * v + 2], pM[4 * v + 3]);
@@ -566,7 +594,8 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, 
                             }
                         } else {
 #pragma unroll
-                            for (int c = 0; c < C; c++) accM[c] = fmaf(FMv[c] * nM[c], fac, accM[c]);
+                            for (int c = 0; c < C; c++)   // (amino: scale first -- F*B of two unscaled values can leave FP32's range)
+                                accM[c] = LANE_EXP ? fmaf(FMv[c] * fac, nM[c], accM[c]) : fmaf(FMv[c] * nM[c], fac, accM[c]);
                         }
 #pragma unroll
                         for (int c = 0; c < C; c++) { sM[c] = nM[c]; sI[c] = nI[c]; sD[c] = nD[c]; }
@@ -588,8 +617,8 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, 
                 if (((tF - 1) & 7) == 0 && tF > 1) {  // next step enters the previous exponent block
                     gFc = gFnext;
                     gblk--;
-                    gFnext = gFs[max(gblk - 1, 0)];
-                    fac = exp2f((float)(gFc + g - gT)) * invT;
+                    gFnext = gFs[GF_AT(max(gblk - 1, 0))];
+                    fac = post_scale(gFc, g);
                 }
             };
             auto brescale = [&](const int tp) {
@@ -600,14 +629,25 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, 
                     // the running B(i) partial carries the mass of every strip to the right, which can be far above
                     // this strip's own cells: it must drive the exponent too (cells that flush are negligible)
                     mx = fmaxf(mx, bp);
+                    if (!LANE_EXP) {
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
+                        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
+                    }
                     int e_need = (mx > 1048576.f) ? fexp(mx) : 0;
                     if (!lastS) {   // exponent the right strip had 8 rows ahead (that block is already in the ring)
                         const int ic = max(Ls - tp, 0), r = max(0, Ls - (tp + W_SCALE_EVERY));
                         const int sl = ((r >> 3) == (ic >> 3)) ? bcur : bnd_next(bcur);
                         const int ahead = lds_i1v(bnd_ring + sl * 256 + (r & 7) * 32 + 16) - 40 - g;
-                        e_need = max(e_need, ahead);
+                        if (!LANE_EXP || lane == 31) e_need = max(e_need, ahead);
+                    }
+                    if (LANE_EXP) {   // couple the lanes: g_l >= g_{l+1} - 16
+                        int need = g + e_need;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int dn = __shfl_down_sync(FULL, need, o);
+                            if (lane + o < 32) need = max(need, dn - 16 * o);
+                        }
+                        e_need = need - g;
                     }
                     if (e_need > 0) {
                         const float f = pow2i(-e_need);
@@ -615,7 +655,7 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, 
 #pragma unroll
                         for (int c = 0; c < C; c++) { sM[c] *= f; sI[c] *= f; sD[c] *= f; }
                         rMb *= f; bp *= f; ebs *= f;
-                        fac = exp2f((float)(gFc + g - gT)) * invT;
+                        fac = post_scale(gFc, g);
                     }
                 }
             };
