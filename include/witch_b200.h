@@ -132,6 +132,22 @@ int witch_graph_align(witch_ehmm *e, int n_queries, const int32_t *qlen, const i
                       const int32_t *nongaps, int backbone_length, const int64_t *row_off, char *rows, int32_t *row_len);
 
 /*
+ * Final transitivity merge == ExtendedAlignment.merge_in applied to every query row in turn
+ * (helpers/alignment_tools.py:1183-1316 driven by gcmm/merger.py:69-78) + remove_insertion_columns (:1140-1156).
+ * Every input row has exactly `backbone_length` regular columns (upper case or '-') and lower-case insertion columns
+ * between them (rows from witch_graph_align); rows flagged is_backbone[r] are taken verbatim (no insertion columns).
+ * Insertion runs of different rows that sit in the same backbone gap are overlaid from the left. All arrays HOST.
+ *   gap_width[backbone_length+1] (out, may be NULL): merged width of every gap's insertion block
+ *   *out_width (out): merged alignment width = backbone_length + sum(gap_width)
+ *   merged (may be NULL): nrows rows of merged_cap_width bytes each (>= *out_width; only the first *out_width are
+ *       written); masked (may be NULL): nrows rows of backbone_length bytes (insertion columns removed).
+ * Call once with merged = masked = NULL to learn *out_width, then again with buffers.
+ */
+int witch_merge_rows(witch_ehmm *e, int nrows, const int64_t *row_off, const int32_t *row_len, const uint8_t *is_backbone,
+                     const char *rows, int backbone_length, int32_t *gap_width, int64_t *out_width, char *merged,
+                     int64_t merged_cap_width, char *masked);
+
+/*
  * Instrumentation for bench.py: number of kernels this library has launched so far in this process and the
  * accumulated device time (ms, CUDA events on the launching stream) of the dominant DP kernels since the last
  * witch_prof_reset(). Timing is only collected while witch_prof_enable(1).

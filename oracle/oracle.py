@@ -294,3 +294,36 @@ def graph_align(seq, backbone_length, subset_to_weight, subset_to_aligned_column
             out.append("-")
     row = "-" * min_col + "".join(out) + "-" * (backbone_length - max_col - 1)
     return row
+
+
+def merge_rows(rows, backbone_length):
+    """helpers/alignment_tools.py:1183-1316 (ExtendedAlignment.merge_in) + gcmm/merger.py:69-78 restated in closed
+    form for the rows WITCH merges: every row has exactly `backbone_length` regular columns (upper case or '-') and
+    any number of insertion columns (lower case) between them. Insertion runs that sit in the same backbone gap are
+    overlaid from the left, so the merged width of gap g is the longest run any row has there; a row's own run is
+    left-aligned in the gap's block and padded with '-'. -> (merged rows, masked rows, gap widths [backbone_length+1])."""
+    B = backbone_length
+    runs = []
+    width = np.zeros(B + 1, dtype=np.int64)
+    for r in rows:
+        g, cur, rr = 0, [], []
+        for ch in r:
+            if "a" <= ch <= "z":
+                cur.append(ch)
+            else:
+                rr.append("".join(cur)); cur = []; g += 1
+        rr.append("".join(cur))
+        assert g == B, (g, B)
+        runs.append(rr)
+        width = np.maximum(width, [len(x) for x in rr])
+    merged, masked = [], []
+    for r, rr in zip(rows, runs):
+        reg = [ch for ch in r if not ("a" <= ch <= "z")]
+        out = []
+        for g in range(B):
+            out.append(rr[g] + "-" * (int(width[g]) - len(rr[g])))
+            out.append(reg[g])
+        out.append(rr[B] + "-" * (int(width[B]) - len(rr[B])))
+        merged.append("".join(out))
+        masked.append("".join(reg))
+    return merged, masked, width

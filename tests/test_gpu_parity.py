@@ -264,3 +264,28 @@ def test_graph_dp_full_device_path_vs_oracle(wb, tmp_path):
         if taxon in G["queries"] and rows[taxon] == G["queries"][taxon]["row"]:
             nsame_ref += 1
     assert nsame_ref >= len(G["queries"]) - 3   # documented: multi-domain-flagged extras / one near-tie alignment
+
+
+def test_merge_matches_reference_python(wb, tmp_path):
+    """Device transitivity merge fed with the reference's own rows must reproduce, character for character, what the
+    reference's ExtendedAlignment.merge_in / remove_insertion_columns produced (tests/golden/make_golden_merge.py)."""
+    import gzip, json
+    from golden_util import GOLDEN
+    from witch_b200.gcmm import mergeAlignmentsCollapsed
+    gold, queries, paths = load_set("dna_small", str(tmp_path))
+    G = _graph_golden()
+    Mg = json.loads(gzip.open(os.path.join(GOLDEN, "dna_small", "merge_golden.json.gz")).read())
+    E = wb.EHMM(paths)
+    qrows = {t: G["queries"][t]["row"] for t in Mg["order"]}
+    out = str(tmp_path / "aligned.fasta")
+    full, mask = mergeAlignmentsCollapsed(E, [tuple(x) for x in Mg["backbone"]], qrows, G["backbone_length"], outpath=out)
+    assert list(full.keys()) == [n for n, _ in Mg["backbone"]] + Mg["order"]
+    for n in full:
+        assert full[n] == Mg["merged"][n], n
+        assert mask[n] == Mg["masked"][n], n
+    assert os.path.exists(out) and os.path.exists(str(tmp_path / "aligned.masked.fasta"))
+    # oracle restatement agrees too, and an empty query set leaves the backbone untouched
+    m2, k2, w2 = O.merge_rows([r for _, r in Mg["backbone"]] + list(qrows.values()), G["backbone_length"])
+    assert m2 == list(full.values()) and k2 == list(mask.values())
+    f0, m0 = mergeAlignmentsCollapsed(E, [tuple(x) for x in Mg["backbone"]], {}, G["backbone_length"])
+    assert list(f0.values()) == [r for _, r in Mg["backbone"]] == list(m0.values())

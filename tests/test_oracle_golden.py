@@ -84,3 +84,17 @@ def test_weights_formula_matches_softmax_form():
 def test_compress_insertions():
     assert O.compress_insertions("--ac-AC-gt-T--g-a-") == "ac---AC-gt-T----ga"
     assert O.compress_insertions("--ac--") == "--ac--"
+
+
+def test_merge_restatement_matches_reference_python():
+    """oracle.merge_rows (closed form) == the reference's ExtendedAlignment.merge_in applied query by query."""
+    import gzip, json, os
+    from golden_util import GOLDEN
+    Mg = json.loads(gzip.open(os.path.join(GOLDEN, "dna_small", "merge_golden.json.gz")).read())
+    G = json.loads(gzip.open(os.path.join(GOLDEN, "dna_small", "graph_golden.json.gz")).read())
+    names = [n for n, _ in Mg["backbone"]] + Mg["order"]
+    rows = [r for _, r in Mg["backbone"]] + [G["queries"][t]["row"] for t in Mg["order"]]
+    merged, masked, width = O.merge_rows(rows, G["backbone_length"])
+    assert len(merged[0]) == G["backbone_length"] + int(width.sum()) > G["backbone_length"]
+    for n, a, b in zip(names, merged, masked):
+        assert a == Mg["merged"][n] and b == Mg["masked"][n], n

@@ -33,6 +33,8 @@ SYMBOLS = {
     "witch_align_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, c_i32p, c_i32p, c_i64p, ctypes.c_void_p, ctypes.c_void_p]),
     "witch_graph_align": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_i32p, c_i64p, ctypes.c_char_p, c_i32p, c_i32p, c_f64p, c_i64p,
                                          c_i32p, ctypes.c_int, c_i64p, c_i32p, c_i32p, ctypes.c_int, c_i64p, ctypes.c_void_p, c_i32p]),
+    "witch_merge_rows": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_i64p, c_i32p, c_u8p, ctypes.c_char_p, ctypes.c_int, c_i32p,
+                                        c_i64p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
     "witch_kernel_launches": (ctypes.c_uint64, []),
     "witch_prof_enable": (None, [ctypes.c_int]),
     "witch_prof_reset": (None, []),

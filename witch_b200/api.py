@@ -188,3 +188,33 @@ def debug_fwdbwd(ehmm, queries, qidx, hidx, multihit):
 
 def kernel_launches():
     return int(_lib.load().witch_kernel_launches())
+
+
+def merge_rows(ehmm, rows, is_backbone, backbone_length, want_masked=True):
+    """Final transitivity merge of aligned rows (gcmm/merger.py:69-78 + helpers/alignment_tools.py:1183-1316, 1140-1156).
+    rows: strings with exactly backbone_length regular columns each; is_backbone[r]: the row is a backbone row.
+    -> (merged rows, masked rows or None, gap widths)."""
+    n = len(rows)
+    row_len = np.array([len(r) for r in rows], dtype=np.int32)
+    row_off = np.zeros(max(n, 1), dtype=np.int64)
+    if n:
+        row_off[1:n] = np.cumsum(row_len[:-1].astype(np.int64))
+    blob = "".join(rows).encode()
+    bb = np.ascontiguousarray(is_backbone, dtype=np.uint8)
+    gw = np.zeros(backbone_length + 1, dtype=np.int32)
+    ow = ctypes.c_int64(0)
+    lib = _lib.load()
+    check(lib.witch_merge_rows(ehmm._h, n, _ptr(row_off, ctypes.c_int64), _ptr(row_len, ctypes.c_int32), _ptr(bb, ctypes.c_uint8),
+                               blob, int(backbone_length), _ptr(gw, ctypes.c_int32), ctypes.byref(ow), None, 0, None))
+    width = int(ow.value)
+    merged = ctypes.create_string_buffer(max(n * width, 1))
+    masked = ctypes.create_string_buffer(max(n * backbone_length, 1)) if want_masked else None
+    check(lib.witch_merge_rows(ehmm._h, n, _ptr(row_off, ctypes.c_int64), _ptr(row_len, ctypes.c_int32), _ptr(bb, ctypes.c_uint8),
+                               blob, int(backbone_length), _ptr(gw, ctypes.c_int32), ctypes.byref(ow), merged, width, masked))
+    raw = merged.raw
+    out = [raw[r * width:(r + 1) * width].decode() for r in range(n)]
+    msk = None
+    if want_masked:
+        rawm = masked.raw
+        msk = [rawm[r * backbone_length:(r + 1) * backbone_length].decode() for r in range(n)]
+    return out, msk, gw

@@ -408,3 +408,63 @@ extern "C" int witch_graph_align(witch_ehmm *e, int nq, const int32_t *qlen, con
         return fail(WITCH_ERR_CUDA, ex.what());
     }
 }
+
+extern "C" int witch_merge_rows(witch_ehmm *e, int nrows, const int64_t *row_off, const int32_t *row_len,
+                                const uint8_t *is_backbone, const char *rows, int backbone_length, int32_t *gap_width,
+                                int64_t *out_width, char *merged, int64_t merged_cap_width, char *masked) {
+    try {
+        if (!e || nrows < 0 || backbone_length <= 0 || !out_width || (nrows > 0 && (!row_off || !row_len || !is_backbone || !rows)))
+            return fail(WITCH_ERR_ARG, "witch_merge_rows: bad arguments");
+        CUDA_TRY(cudaSetDevice(e->device));
+        const int B = backbone_length;
+        long long total = 0;
+        for (int r = 0; r < nrows; r++) {
+            if (row_len[r] < 0 || row_off[r] < 0) return fail(WITCH_ERR_ARG, "witch_merge_rows: negative row offset/length");
+            total = std::max<long long>(total, row_off[r] + row_len[r]);
+        }
+        DevBuf<long long> d_ro, d_gs;
+        DevBuf<int> d_rl, d_w;
+        DevBuf<uint8_t> d_bb;
+        DevBuf<char> d_rows, d_out, d_msk;
+        std::vector<long long> ro(row_off, row_off + nrows);
+        auto up = [&](auto &buf, const auto *src, size_t n) {
+            buf.alloc(n);
+            if (n) CUDA_TRY(cudaMemcpy(buf.p, src, n * sizeof(*src), cudaMemcpyHostToDevice));
+        };
+        up(d_ro, ro.data(), nrows); up(d_rl, row_len, nrows); up(d_bb, is_backbone, nrows); up(d_rows, rows, (size_t)total);
+        d_w.alloc(B + 1); d_gs.alloc(B + 2);
+        CUDA_TRY(cudaMemset(d_w.p, 0, (size_t)(B + 1) * sizeof(int)));
+        MergeWork W;
+        W.nrows = nrows; W.row_off = d_ro.p; W.row_len = d_rl.p; W.is_backbone = d_bb.p; W.rows = d_rows.p; W.B = B;
+        W.width = d_w.p; W.gap_start = d_gs.p; W.out = nullptr; W.masked = nullptr; W.out_width = 0;
+        const int grid = std::max(1, (nrows + 3) / 4);
+        if (nrows > 0) {
+            merge_rows_kernel<false><<<grid, 128>>>(W);
+            g_launches++;
+        }
+        merge_scan_kernel<<<1, 1024>>>(d_w.p, B, d_gs.p);
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+        long long width_total = 0;
+        CUDA_TRY(cudaMemcpy(&width_total, d_gs.p + (B + 1), sizeof(long long), cudaMemcpyDeviceToHost));
+        *out_width = width_total;
+        if (gap_width) CUDA_TRY(cudaMemcpy(gap_width, d_w.p, (size_t)(B + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+        if (!merged && !masked) return WITCH_OK;   // plan only: the caller sizes its buffers from *out_width
+        if (merged && merged_cap_width < width_total) return fail(WITCH_ERR_ARG, "witch_merge_rows: merged buffer narrower than the merged width");
+        if (nrows == 0) return WITCH_OK;
+        d_out.alloc((size_t)nrows * (size_t)width_total);
+        if (masked) d_msk.alloc((size_t)nrows * (size_t)B);
+        if (masked) CUDA_TRY(cudaMemset(d_msk.p, '-', (size_t)nrows * (size_t)B));
+        W.out = d_out.p; W.masked = masked ? d_msk.p : nullptr; W.out_width = width_total;
+        merge_rows_kernel<true><<<grid, 128>>>(W);
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+        if (merged)
+            CUDA_TRY(cudaMemcpy2D(merged, (size_t)merged_cap_width, d_out.p, (size_t)width_total, (size_t)width_total, (size_t)nrows,
+                                  cudaMemcpyDeviceToHost));
+        if (masked) CUDA_TRY(cudaMemcpy(masked, d_msk.p, (size_t)nrows * (size_t)B, cudaMemcpyDeviceToHost));
+        return WITCH_OK;
+    } catch (const std::exception &ex) {
+        return fail(WITCH_ERR_CUDA, ex.what());
+    }
+}

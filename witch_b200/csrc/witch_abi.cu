@@ -19,6 +19,7 @@
 #include "wave_kernels.cuh"
 #include "post_kernels.cuh"
 #include "graph_kernel.cuh"
+#include "merge_kernel.cuh"
 
 using namespace witch;
 

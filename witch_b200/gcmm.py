@@ -155,6 +155,30 @@ class BatchedSearch:
         return self._seqs[q].upper()
 
 
+def mergeAlignmentsCollapsed(ehmm, backbone_items, query_rows, backbone_length, outpath=None, renamed_taxa=None):
+    """gcmm/merger.py:42-102 mirror: merge every query row (the dict alignSubQueriesNew returns) into the backbone
+    alignment with transitivity, singleton insertions collapsed in lower case (UPP style); the masked version has
+    the insertion columns removed. backbone_items: [(name, aligned row)]. Names renamed by the reference's loader
+    (renamed_taxa: original -> renamed) are mapped back. When `outpath` is given both FASTA files are written with
+    the reference's naming rule (<name>.masked.<suffix>). -> (merged dict, masked dict), backbone rows first, then the
+    queries in insertion order -- the order merge_in's dict update produces."""
+    names = [n for n, _ in backbone_items] + list(query_rows.keys())
+    rows = [r for _, r in backbone_items] + list(query_rows.values())
+    flags = [1] * len(backbone_items) + [0] * len(query_rows)
+    merged, masked, _ = api.merge_rows(ehmm, rows, flags, backbone_length)
+    back = {v: k for k, v in (renamed_taxa or {}).items()}
+    names = [back.get(n, n) for n in names]
+    full, mask = dict(zip(names, merged)), dict(zip(names, masked))
+    if outpath:
+        suffix = outpath.split(".")[-1]
+        masked_outpath = ".".join(outpath.split(".")[:-1]) + ".masked." + suffix if suffix in ("fa", "fasta") else outpath + ".masked.fasta"
+        for path, d in ((outpath, full), (masked_outpath, mask)):
+            with open(path, "w") as f:
+                for n, r in d.items():
+                    f.write(">{}\n{}\n".format(n, r))
+    return full, mask
+
+
 def writeWeightsToLocal(taxon_to_weights, path):
     """weighting.py:174-178; plain floats (not numpy reprs) so that readWeightsFromLocal's eval works everywhere."""
     with open(path, "w") as f:
