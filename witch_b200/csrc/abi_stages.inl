@@ -1,4 +1,16 @@
 // Stage orchestration behind the C ABI (included by witch_abi.cu).
+#include <chrono>
+struct HostClock {   // WITCH_TIMING=1: wall-clock of the host-side phases of a call, to stderr
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    bool on = getenv("WITCH_TIMING") != nullptr;
+    void lap(const char *what) {
+        if (!on) return;
+        cudaDeviceSynchronize();
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[witch timing] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 static int wave_C_for(const witch_ehmm *) { return 8; }
 
@@ -12,13 +24,11 @@ static void run_wave_c(witch_ehmm *e, witch_queries *q, std::vector<WaveItem> it
     const int SW = 32 * C;
     // buckets by envelope length so that scratch is not sized by the single longest item
     const int caps[] = {256, 512, 1024, 2048, 4096, 1 << 30};
-    // ... and by model size class, so that the shared-memory emission table of the few long models (the root of the
-    // decomposition holds every backbone column) does not set the occupancy of everything else
-    std::vector<WaveBucket> buckets(12);
+    std::vector<WaveBucket> buckets(6);
     for (auto &it : items) {
         int b = 0;
         while (it.Ls > caps[b]) b++;
-        buckets[2 * b].items.push_back(it);
+        buckets[b].items.push_back(it);
     }
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
@@ -33,10 +43,23 @@ static void run_wave_c(witch_ehmm *e, witch_queries *q, std::vector<WaveItem> it
             cells += (double)it.Ls * e->M[it.h];
         }
         max_strips = (maxM + SW - 1) / SW;
-        std::stable_sort(bk.items.begin(), bk.items.end(), [&](const WaveItem &a, const WaveItem &b) {
-            if (a.h != b.h) return e->M[a.h] != e->M[b.h] ? e->M[a.h] > e->M[b.h] : a.h < b.h;
-            return a.Ls > b.Ls;
-        });
+        // order: longer models first, then by HMM, then longer envelopes first -- two stable counting passes (LSD radix:
+        // millions of items for protein-sized workloads make a comparison sort the largest host cost of a step)
+        {
+            std::vector<int> hrank(e->H), horder(e->H);
+            std::iota(horder.begin(), horder.end(), 0);
+            std::stable_sort(horder.begin(), horder.end(), [&](int a, int b) { return e->M[a] > e->M[b]; });
+            for (int r = 0; r < e->H; r++) hrank[horder[r]] = r;
+            std::vector<WaveItem> tmp(bk.items.size());
+            std::vector<size_t> cnt((size_t)Lcap + 2, 0);
+            for (auto &it : bk.items) cnt[Lcap - it.Ls + 1]++;                 // key 2: Ls descending
+            for (size_t k = 1; k < cnt.size(); k++) cnt[k] += cnt[k - 1];
+            for (auto &it : bk.items) tmp[cnt[Lcap - it.Ls]++] = it;
+            cnt.assign((size_t)e->H + 1, 0);
+            for (auto &it : tmp) cnt[hrank[it.h] + 1]++;                       // key 1: model rank
+            for (size_t k = 1; k < cnt.size(); k++) cnt[k] += cnt[k - 1];
+            for (auto &it : tmp) bk.items[cnt[hrank[it.h]]++] = it;
+        }
         std::vector<int> gfirst, gcount;
         for (size_t i = 0; i < bk.items.size();) {
             size_t j = i;
@@ -107,11 +130,14 @@ extern "C" int witch_score_dev(witch_ehmm *e, witch_queries *q, float *d_scores,
         std::vector<int> qs(nq), hs(H);
         std::iota(qs.begin(), qs.end(), 0);
         std::iota(hs.begin(), hs.end(), 0);
+        HostClock hc;
         run_parser(e, q, qs, hs, nullptr, st);
+        hc.lap("parser");
         // envelope list -> wave items (host side)
         std::vector<PairParse> parse((size_t)nq * H);
         CUDA_TRY(cudaMemcpyAsync(parse.data(), e->parse.p, parse.size() * sizeof(PairParse), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
+        hc.lap("parse D2H");
         std::vector<int> env_base((size_t)nq * H, 0);
         std::vector<WaveItem> items;
         for (int qi = 0; qi < nq; qi++)
@@ -125,10 +151,13 @@ extern "C" int witch_score_dev(witch_ehmm *e, witch_queries *q, float *d_scores,
                     items.push_back(it);
                 }
             }
+        hc.lap("build items");
         e->f1.alloc(items.size() + 1);
         e->f2.alloc(items.size() + 1);
         e->i3.upload(env_base, st);
-        run_wave<false>(e, q, items, e->f1.p, e->f2.p, nullptr, nullptr, nullptr, nullptr, st);
+        hc.lap("upload env_base");
+        run_wave<false>(e, q, std::move(items), e->f1.p, e->f2.p, nullptr, nullptr, nullptr, nullptr, st);
+        hc.lap("run_wave (all buckets)");
         const long long np = (long long)nq * H;
         finalize_scores_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(e->parse.p, q->dlen.p, nq, H, e->i3.p, e->f1.p,
                                                                            e->f2.p, d_scores, d_reported, d_pre, d_flags);
