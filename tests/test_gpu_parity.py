@@ -289,3 +289,40 @@ def test_merge_matches_reference_python(wb, tmp_path):
     assert m2 == list(full.values()) and k2 == list(mask.values())
     f0, m0 = mergeAlignmentsCollapsed(E, [tuple(x) for x in Mg["backbone"]], {}, G["backbone_length"])
     assert list(f0.values()) == [r for _, r in Mg["backbone"]] == list(m0.values())
+
+
+def test_next_rows_at_scale_vs_oracle(wb, tmp_path):
+    """score -> weights -> align -> graph DP -> transitivity merge on a workload the golden sets do not cover (longer
+    models, 40+ HMMs, hundreds of queries): properties that hold for every row, the oracle on a sample, and the
+    merged alignment against the oracle's closed form."""
+    import synth
+    from witch_b200.gcmm import BatchedSearch, mergeAlignmentsCollapsed
+    wl = synth.make_workload(str(tmp_path), alphabet="dna", n_total=1500, n_backbone=200, root_len=900, decomp=10,
+                             frag_frac=0.5, frag_mean=300, seed=11)
+    B = wl["backbone_length"]
+    names, seqs = wl["names"][:400], wl["seqs"][:400]
+    bs = BatchedSearch(wl["hmm_paths"], num_hmms=10)
+    bs.search(names, seqs)
+    t2w = bs.writeWeights()
+    ret = {h: wl["retained_columns"][h] for h in range(len(wl["hmm_paths"]))}
+    ng = {h: wl["nongaps_per_column"][h] for h in range(len(wl["hmm_paths"]))}
+    rows = bs.alignSubQueriesNew(B, ret, ng, t2w)
+    assert len(rows) == len(t2w) > 390
+    qd = dict(zip(names, seqs))
+    for t, r in rows.items():
+        assert r.replace("-", "").upper() == qd[t]                       # every residue exactly once, in order
+        assert sum(1 for ch in r if not ("a" <= ch <= "z")) == B          # exactly one cell per backbone column
+    bb = bs.getBackbones(t2w)
+    rng = np.random.default_rng(5)
+    for t in rng.choice(sorted(rows), 25, replace=False):
+        _, wmap, s2c = bb[t]
+        want = O.compress_insertions(O.graph_align(qd[t], B, wmap, s2c, ret, ng))
+        assert rows[t] == want, t
+    backbone = [("bb0", "A" * B), ("bb1", "-" * (B // 2) + "C" * (B - B // 2))]
+    full, mask = mergeAlignmentsCollapsed(bs.ehmm, backbone, rows, B)
+    m2, k2, w2 = O.merge_rows([r for _, r in backbone] + list(rows.values()), B)
+    assert list(full.values()) == m2 and list(mask.values()) == k2
+    width = B + int(w2.sum())
+    assert all(len(r) == width for r in full.values()) and all(len(r) == B for r in mask.values())
+    for t, r in rows.items():
+        assert full[t].replace("-", "").upper() == qd[t] and mask[t] == "".join(ch for ch in r if not ("a" <= ch <= "z"))
