@@ -328,6 +328,11 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser_kernel(DevEhmm E, DevQue
         const float fwd_bits = log2f(Tm) + (float)sT;
 
         // =========================== Backward ===========================
+        // Two barriers per row. B_b(i) = sum_k Mb(i+1,k) e_k entry_k and the D->D scan are both functions of row
+        // i+1 only once the exit injection E_b(i) is split off by linearity: D_b(i,k) = D'(k) + E_b(i) * gD[k], with D'
+        // the chain driven by the match terms alone and gD[k] = 1 + tDD[k] gD[k+1] a model constant. So the B sum and
+        // the scan of D' run side by side before the barrier; after it E_b(i), the scan total and the finished row
+        // follow, and a second barrier hands the first-column Mb to the left neighbour warp.
         // parameters leaving the owned columns
         load_cols<C>(E.tMM + po, k0 + 1, pa);
         load_cols<C>(E.tIM + po, k0 + 1, pb);
@@ -335,12 +340,12 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser_kernel(DevEhmm E, DevQue
         load_cols<C>(E.tMD + po, k0 + 1, pmd);
         load_cols<C>(E.tDD + po, k0 + 1, pdd);
         // pmi, pii, pen already hold tMI, tII, entry of the owned columns
-        pDD[C - 1] = pdd[C - 1];
-#pragma unroll
-        for (int c = C - 2; c >= 0; c--) pDD[c] = pdd[c] * pDD[c + 1];
-        __syncthreads();  // everyone done reading s_pw / s_es of the forward pass
+        const float GX = __ldg(E.gD + po + k0 + C + 1);   // D response of the right neighbour's first column to a unit exit
+        __syncthreads();  // everyone done reading the forward pass's reduction rows
         {
-            float Pc = pDD[0];
+            float Pc = pdd[0];
+#pragma unroll
+            for (int c = 1; c < C; c++) Pc *= pdd[c];
 #pragma unroll
             for (int s = 0; s < 5; s++) {
                 float dn = __shfl_down_sync(0xffffffffu, Pc, 1 << s);
@@ -352,10 +357,10 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser_kernel(DevEhmm E, DevQue
             if (lane == 0) sts_f1(SA_PW(w), Pc);
         }
         __syncthreads();
-        czl = 0.f;  // Z_w = sum_{l > w} tot[l] * prod_{w < w'' < l} PW[w'']
-        if (lane > w && lane < NW) {
+        czl = 0.f;  // Z_w = sum_{l > w} tot[l] * prod_{w < w'' < l} PW[w'']   (lane lw stands for warp lw)
+        if (lw > w && lw < NW) {
             czl = 1.f;
-            for (int ww = w + 1; ww < lane; ww++) czl *= lds_f1v(SA_PW(ww));
+            for (int ww = w + 1; ww < lw; ww++) czl *= lds_f1v(SA_PW(ww));
         }
 #pragma unroll
         for (int c = 0; c < C; c++) { sM[c] = 0.f; sI[c] = 0.f; sD[c] = 0.f; }
@@ -365,7 +370,8 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser_kernel(DevEhmm E, DevQue
         float4 *bsrow = reinterpret_cast<float4 *>(Bs + 8 * L);
         PIN64(bsrow);
         for (int i = L; i >= 0; i--) {
-            // pre(i): consume row i+1 and residue i+1
+            // ---- before the barrier: everything that depends on row i+1 only ----
+            const unsigned par = (i & 1) * 128;
             float mn[C], mnR[C];
             float eR = 0.f;
             if (i < L) {
@@ -392,9 +398,6 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser_kernel(DevEhmm E, DevQue
                 mnR[c] = (c < C - 1) ? mn[c + 1] : nb;
                 bp = fmaf(mn[c], pen[c], bp);
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) bp += __shfl_xor_sync(0xffffffffu, bp, o);
-            if (lane == 0) sts_f1(SA_ES(w), bp);
             float Mp[C], nI[C], tm[C];
 #pragma unroll
             for (int c = 0; c < C; c++) {
@@ -402,21 +405,37 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser_kernel(DevEhmm E, DevQue
                 nI[c] = fmaf(mnR[c], pb[c], sI[c] * pii[c]);
                 tm[c] = mnR[c] * pg[c];
             }
-            __syncthreads();
-            // mid(i)
-            float Bi = (lane < NW) ? lds_f1v(SA_ES(lane)) : 0.f;
+            float y = tm[C - 1];   // D' chain (match terms only); its output at the thread's first column feeds the scan
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) Bi += __shfl_xor_sync(0xffffffffu, Bi, o);
+            for (int c = C - 2; c >= 0; c--) y = fmaf(y, pdd[c], tm[c]);
+#pragma unroll
+            for (int s = 0; s < 5; s++) {   // warp reduction of the B partial and the D' scan side by side
+                const float dn = __shfl_down_sync(0xffffffffu, y, 1 << s);
+                bp += __shfl_xor_sync(0xffffffffu, bp, 1 << s);
+                y = fmaf(coef[s], dn, y);
+            }
+            float yex = __shfl_down_sync(0xffffffffu, y, 1);
+            if (lane == 31) yex = 0.f;
+            if (lane == 0) { sts_f1(SA_ES2(par, w), bp); sts_f1(SA_TOT2(par, w), y); }
+            __syncthreads();
+            // ---- after it: E_b(i), the scan total, the finished row ----
+            float Bi = lds_f1v(SA_ES2(par, lw)), Z = lds_f1v(SA_TOT2(par, lw)) * czl;   // (slots >= NW hold zeros)
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                Bi += __shfl_xor_sync(0xffffffffu, Bi, o);
+                Z += __shfl_xor_sync(0xffffffffu, Z, o);
+            }
             if (i == L) { bC = pmove; bJ = 0.f; bN = 0.f; }
             else { bJ = bJ * ploop + Bi * pmove; bC = bC * ploop; bN = bN * ploop + Bi * pmove; }
             bE = bJ * EJ + bC * EC;
+            float Xp = fmaf(Cexcl, Z, yex);   // D' entering from the right neighbour's first column
             {
                 float big = fmaxf(fmaxf(bN, bJ), Bi);
                 if (big > 1.0e9f) {
                     int e = fexp(big);
                     float scl = pow2i(-e);
                     sB += e;
-                    bN *= scl; bJ *= scl; bC *= scl; bE *= scl; Bi *= scl;
+                    bN *= scl; bJ *= scl; bC *= scl; bE *= scl; Bi *= scl; Xp *= scl;
 #pragma unroll
                     for (int c = 0; c < C; c++) { Mp[c] *= scl; nI[c] *= scl; tm[c] *= scl; }
                 }
@@ -426,29 +445,11 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser_kernel(DevEhmm E, DevQue
             }
             bsrow -= 2;
             if (i == 0) break;
-            float dl[C];
-            dl[C - 1] = tm[C - 1] + bE;
-#pragma unroll
-            for (int c = C - 2; c >= 0; c--) dl[c] = fmaf(dl[c + 1], pdd[c], tm[c] + bE);
-            float y = dl[0];
-#pragma unroll
-            for (int s = 0; s < 5; s++) {
-                float dn = __shfl_down_sync(0xffffffffu, y, 1 << s);
-                y = fmaf(coef[s], dn, y);
-            }
-            float yex = __shfl_down_sync(0xffffffffu, y, 1);
-            if (lane == 31) yex = 0.f;
-            if (lane == 0) sts_f1(SA_TOT(w), y);
-            __syncthreads();
-            // post(i)
-            float Z = (lane < NW) ? lds_f1v(SA_TOT(lane)) * czl : 0.f;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) Z += __shfl_xor_sync(0xffffffffu, Z, o);
-            const float X = fmaf(Cexcl, Z, yex);  // D(i, first column of the right neighbour)
+            const float X = fmaf(bE, GX, Xp);  // D(i, first column of the right neighbour)
 #pragma unroll
             for (int c = C - 1; c >= 0; c--) {
-                sD[c] = fmaf(pDD[c], X, dl[c]);
                 const float dr = (c < C - 1) ? sD[c + 1] : X;
+                sD[c] = fmaf(pdd[c], dr, tm[c] + bE);
                 sM[c] = fmaf(pmd[c], dr, Mp[c] + bE);
                 sI[c] = nI[c];
             }
