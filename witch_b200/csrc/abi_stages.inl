@@ -16,20 +16,47 @@ static int wave_C_for(const witch_ehmm *) { return 8; }
 
 struct WaveBucket { int Lcap; std::vector<WaveItem> items; };
 
-// Launches the wavefront kernel over `items` (any order); outputs indexed by WaveItem::pair.
-template <bool ALIGN, int C, int WAVE_WARPS, int MINB, int RING, bool LANE_EXP>
-static void run_wave_c(witch_ehmm *e, witch_queries *q, std::vector<WaveItem> items, float *d_envsc, float *d_domcorr,
-                     int *d_cols, const long long *d_coloff, float *d_dbg_fwd, float *d_dbg_bwd, cudaStream_t st) {
-    if (items.empty()) return;
-    const int SW = 32 * C;
-    // buckets by envelope length so that scratch is not sized by the single longest item
-    const int caps[] = {256, 512, 1024, 2048, 4096, 1 << 30};
+// Length classes of the wavefront launches (scratch and residue staging are sized by the longest item of a launch).
+static const int WAVE_CAPS[] = {256, 512, 1024, 2048, 4096, 1 << 30};
+static inline int wave_bucket_of(int Ls) { int b = 0; while (Ls > WAVE_CAPS[b]) b++; return b; }
+
+// rank of every HMM in launch order: longer models first (stable)
+static std::vector<int> model_rank(const witch_ehmm *e) {
+    std::vector<int> hrank(e->H), horder(e->H);
+    std::iota(horder.begin(), horder.end(), 0);
+    std::stable_sort(horder.begin(), horder.end(), [&](int a, int b) { return e->M[a] > e->M[b]; });
+    for (int r = 0; r < e->H; r++) hrank[horder[r]] = r;
+    return hrank;
+}
+
+// Generic path (align stage, debug hooks): bucket by length, then order each bucket by (model rank, longer envelopes
+// first) with two stable counting passes (LSD radix; no comparison sort over millions of items).
+static std::vector<WaveBucket> bucketize_items(const witch_ehmm *e, const std::vector<WaveItem> &items) {
     std::vector<WaveBucket> buckets(6);
-    for (auto &it : items) {
-        int b = 0;
-        while (it.Ls > caps[b]) b++;
-        buckets[b].items.push_back(it);
+    for (auto &it : items) buckets[wave_bucket_of(it.Ls)].items.push_back(it);
+    const std::vector<int> hrank = model_rank(e);
+    for (auto &bk : buckets) {
+        if (bk.items.empty()) continue;
+        int Lcap = 0;
+        for (auto &it : bk.items) Lcap = std::max(Lcap, it.Ls);
+        std::vector<WaveItem> tmp(bk.items.size());
+        std::vector<size_t> cnt((size_t)Lcap + 2, 0);
+        for (auto &it : bk.items) cnt[Lcap - it.Ls + 1]++;                 // key 2: Ls descending
+        for (size_t k = 1; k < cnt.size(); k++) cnt[k] += cnt[k - 1];
+        for (auto &it : bk.items) tmp[cnt[Lcap - it.Ls]++] = it;
+        cnt.assign((size_t)e->H + 1, 0);
+        for (auto &it : tmp) cnt[hrank[it.h] + 1]++;                       // key 1: model rank
+        for (size_t k = 1; k < cnt.size(); k++) cnt[k] += cnt[k - 1];
+        for (auto &it : tmp) bk.items[cnt[hrank[it.h]]++] = it;
     }
+    return buckets;
+}
+
+// Launches the wavefront kernel over pre-ordered buckets (items of one HMM contiguous); outputs indexed by WaveItem::pair.
+template <bool ALIGN, int C, int WAVE_WARPS, int MINB, int RING, bool LANE_EXP>
+static void run_wave_c(witch_ehmm *e, witch_queries *q, std::vector<WaveBucket> &buckets, float *d_envsc, float *d_domcorr,
+                     int *d_cols, const long long *d_coloff, float *d_dbg_fwd, float *d_dbg_bwd, cudaStream_t st) {
+    const int SW = 32 * C;
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
     const double budget = std::min<double>(64.0e9, 0.5 * (double)(free_b + e->bytes.n));
@@ -43,23 +70,6 @@ static void run_wave_c(witch_ehmm *e, witch_queries *q, std::vector<WaveItem> it
             cells += (double)it.Ls * e->M[it.h];
         }
         max_strips = (maxM + SW - 1) / SW;
-        // order: longer models first, then by HMM, then longer envelopes first -- two stable counting passes (LSD radix:
-        // millions of items for protein-sized workloads make a comparison sort the largest host cost of a step)
-        {
-            std::vector<int> hrank(e->H), horder(e->H);
-            std::iota(horder.begin(), horder.end(), 0);
-            std::stable_sort(horder.begin(), horder.end(), [&](int a, int b) { return e->M[a] > e->M[b]; });
-            for (int r = 0; r < e->H; r++) hrank[horder[r]] = r;
-            std::vector<WaveItem> tmp(bk.items.size());
-            std::vector<size_t> cnt((size_t)Lcap + 2, 0);
-            for (auto &it : bk.items) cnt[Lcap - it.Ls + 1]++;                 // key 2: Ls descending
-            for (size_t k = 1; k < cnt.size(); k++) cnt[k] += cnt[k - 1];
-            for (auto &it : bk.items) tmp[cnt[Lcap - it.Ls]++] = it;
-            cnt.assign((size_t)e->H + 1, 0);
-            for (auto &it : tmp) cnt[hrank[it.h] + 1]++;                       // key 1: model rank
-            for (size_t k = 1; k < cnt.size(); k++) cnt[k] += cnt[k - 1];
-            for (auto &it : tmp) bk.items[cnt[hrank[it.h]]++] = it;
-        }
         std::vector<int> gfirst, gcount;
         for (size_t i = 0; i < bk.items.size();) {
             size_t j = i;
@@ -104,13 +114,21 @@ static void run_wave_c(witch_ehmm *e, witch_queries *q, std::vector<WaveItem> it
 }
 
 template <bool ALIGN>
-static void run_wave(witch_ehmm *e, witch_queries *q, std::vector<WaveItem> items, float *d_envsc, float *d_domcorr,
+static void run_wave(witch_ehmm *e, witch_queries *q, std::vector<WaveBucket> &buckets, float *d_envsc, float *d_domcorr,
                      int *d_cols, const long long *d_coloff, float *d_dbg_fwd, float *d_dbg_bwd, cudaStream_t st) {
-#define WV_ARGS e, q, std::move(items), d_envsc, d_domcorr, d_cols, d_coloff, d_dbg_fwd, d_dbg_bwd, st
+#define WV_ARGS e, q, buckets, d_envsc, d_domcorr, d_cols, d_coloff, d_dbg_fwd, d_dbg_bwd, st
     const bool lane_exp = e->alph == ALPH_AMINO;  // per-lane scaling exponents (see wave_kernels.cuh)
     if (ALIGN) { if (lane_exp) run_wave_c<true, 8, 4, 2, 3, true>(WV_ARGS); else run_wave_c<true, 8, 4, 2, 3, false>(WV_ARGS); }
     else { if (lane_exp) run_wave_c<false, 8, 4, 3, 3, true>(WV_ARGS); else run_wave_c<false, 8, 4, 3, 3, false>(WV_ARGS); }
 #undef WV_ARGS
+}
+
+template <bool ALIGN>
+static void run_wave(witch_ehmm *e, witch_queries *q, const std::vector<WaveItem> &items, float *d_envsc, float *d_domcorr,
+                     int *d_cols, const long long *d_coloff, float *d_dbg_fwd, float *d_dbg_bwd, cudaStream_t st) {
+    if (items.empty()) return;
+    std::vector<WaveBucket> buckets = bucketize_items(e, items);
+    run_wave<ALIGN>(e, q, buckets, d_envsc, d_domcorr, d_cols, d_coloff, d_dbg_fwd, d_dbg_bwd, st);
 }
 
 static void check_handles(witch_ehmm *e, witch_queries *q) {
@@ -138,6 +156,7 @@ extern "C" int witch_score_dev(witch_ehmm *e, witch_queries *q, float *d_scores,
         CUDA_TRY(cudaMemcpyAsync(parse.data(), e->parse.p, parse.size() * sizeof(PairParse), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         hc.lap("parse D2H");
+        // work list of the envelope stage; env_base[p] = first output slot of pair p
         std::vector<int> env_base((size_t)nq * H, 0);
         std::vector<WaveItem> items;
         for (int qi = 0; qi < nq; qi++)
@@ -151,12 +170,13 @@ extern "C" int witch_score_dev(witch_ehmm *e, witch_queries *q, float *d_scores,
                     items.push_back(it);
                 }
             }
+        const size_t nitems = items.size();
         hc.lap("build items");
-        e->f1.alloc(items.size() + 1);
-        e->f2.alloc(items.size() + 1);
+        e->f1.alloc(nitems + 1);
+        e->f2.alloc(nitems + 1);
         e->i3.upload(env_base, st);
         hc.lap("upload env_base");
-        run_wave<false>(e, q, std::move(items), e->f1.p, e->f2.p, nullptr, nullptr, nullptr, nullptr, st);
+        run_wave<false>(e, q, items, e->f1.p, e->f2.p, nullptr, nullptr, nullptr, nullptr, st);
         hc.lap("run_wave (all buckets)");
         const long long np = (long long)nq * H;
         finalize_scores_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(e->parse.p, q->dlen.p, nq, H, e->i3.p, e->f1.p,
