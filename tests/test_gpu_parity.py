@@ -326,3 +326,41 @@ def test_next_rows_at_scale_vs_oracle(wb, tmp_path):
     assert all(len(r) == width for r in full.values()) and all(len(r) == B for r in mask.values())
     for t, r in rows.items():
         assert full[t].replace("-", "").upper() == qd[t] and mask[t] == "".join(ch for ch in r if not ("a" <= ch <= "z"))
+
+
+def test_limits_long_queries_and_model_size(wb, tmp_path):
+    """Sizes at the edges: queries far longer than any length class boundary (residue staging and scratch are sized per
+    launch), and a model beyond the supported 3,840 nodes must be refused loudly, not mis-scored."""
+    import synth
+    gold, queries, paths = load_set("dna_small", str(tmp_path))
+    rng = np.random.default_rng(9)
+    base = queries[0][1].upper()
+    long1 = "".join(rng.choice(list("ACGT"), 2500)) + base + "".join(rng.choice(list("ACGT"), 2600))   # 5,000+ nt, one hit
+    long2 = (base + "".join(rng.choice(list("ACGT"), 700))) * 3                                          # three copies
+    E = wb.EHMM(paths[:2])
+    Q = wb.Queries(E, [long1, long2, base])
+    sc, rep, pre, fl = wb.score(E, Q)
+    for h in range(2):
+        prof = O.Profile(paths[h])
+        for qi, s in enumerate([long1, long2, base]):
+            r = O.score_pair(prof, prof.abc.digitize(s))
+            assert bool(rep[qi, h]) == r["reported"], (qi, h)
+            assert abs(pre[qi, h] - r["pre_score"]) < SCORE_TOL_BITS
+            if r["reported"] and r["nregions"] <= 6:
+                assert abs(sc[qi, h] - r["score"]) < SCORE_TOL_BITS, (qi, h, sc[qi, h], r)
+    cols = wb.align(E, Q, [0, 1], [0, 0])
+    prof = O.Profile(paths[0])
+    for c, s in zip(cols, [long1, long2]):
+        ref = O.align_pair(prof, prof.abc.digitize(s))
+        assert len(c) == len(s) and int((c != ref).sum()) <= 1
+    # a 4,000-node model is outside the supported range of the parser kernels
+    M = 4000
+    cons = rng.integers(0, 4, M)
+    counts = np.zeros((M, 4)); counts[np.arange(M), cons] = 1.0
+    tc = np.zeros((M + 1, 4)); tc[:, 0] = 1.0
+    big = str(tmp_path / "big.hmm")
+    synth.write_hmm(big, "big", counts, tc, 1, synth.DNA)
+    Eb = wb.EHMM([big])
+    Qb = wb.Queries(Eb, ["ACGT" * 50])
+    with pytest.raises(wb.WitchError, match="3840"):
+        wb.score(Eb, Qb)
