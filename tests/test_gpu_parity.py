@@ -353,8 +353,29 @@ def test_limits_long_queries_and_model_size(wb, tmp_path):
     for c, s in zip(cols, [long1, long2]):
         ref = O.align_pair(prof, prof.abc.digitize(s))
         assert len(c) == len(s) and int((c != ref).sum()) <= 1
-    # a 4,000-node model is outside the supported range of the parser kernels
-    M = 4000
+    # a 6,000-node model (slow parser class, own wave launches) still scores and aligns like the oracle
+    M = 6000
+    cons = rng.integers(0, 4, M)
+    counts = np.zeros((M, 4)); counts[np.arange(M), cons] = 1.0
+    tc = np.zeros((M + 1, 4)); tc[:, 0] = 1.0
+    mid = str(tmp_path / "mid.hmm")
+    synth.write_hmm(mid, "mid", counts, tc, 1, synth.DNA)
+    Em = wb.EHMM([mid, paths[0]])
+    frag = "".join(synth.DNA[c] for c in cons[2000:2600])
+    qs = [frag, frag[:200] + "ACGTTGCA" * 5 + frag[200:], base]
+    Qm = wb.Queries(Em, qs)
+    scm, repm, prem, flm = wb.score(Em, Qm)
+    pm = O.Profile(mid)
+    for qi, s_ in enumerate(qs):
+        r = O.score_pair(pm, pm.abc.digitize(s_))
+        assert bool(repm[qi, 0]) == r["reported"] and abs(prem[qi, 0] - r["pre_score"]) < SCORE_TOL_BITS
+        if r["reported"]:
+            assert abs(scm[qi, 0] - r["score"]) < SCORE_TOL_BITS, (qi, scm[qi, 0], r)
+    cm = wb.align(Em, Qm, [0, 1], [0, 0])
+    for c, s_ in zip(cm, qs[:2]):
+        assert int((c != O.align_pair(pm, pm.abc.digitize(s_))).sum()) <= 1
+    # a 9,000-node model is outside the supported range of the parser kernels
+    M = 9000
     cons = rng.integers(0, 4, M)
     counts = np.zeros((M, 4)); counts[np.arange(M), cons] = 1.0
     tc = np.zeros((M + 1, 4)); tc[:, 0] = 1.0
@@ -362,5 +383,5 @@ def test_limits_long_queries_and_model_size(wb, tmp_path):
     synth.write_hmm(big, "big", counts, tc, 1, synth.DNA)
     Eb = wb.EHMM([big])
     Qb = wb.Queries(Eb, ["ACGT" * 50])
-    with pytest.raises(wb.WitchError, match="3840"):
+    with pytest.raises(wb.WitchError, match="8192"):
         wb.score(Eb, Qb)

@@ -32,8 +32,10 @@ static std::vector<int> model_rank(const witch_ehmm *e) {
 // Generic path (align stage, debug hooks): bucket by length, then order each bucket by (model rank, longer envelopes
 // first) with two stable counting passes (LSD radix; no comparison sort over millions of items).
 static std::vector<WaveBucket> bucketize_items(const witch_ehmm *e, const std::vector<WaveItem> &items) {
-    std::vector<WaveBucket> buckets(6);
-    for (auto &it : items) buckets[wave_bucket_of(it.Ls)].items.push_back(it);
+    // 6 length classes x 2 model-size classes: models beyond 13 strips (3,328 nodes) get their own launches so that
+    // their shared-memory emission table does not set the occupancy of everything else
+    std::vector<WaveBucket> buckets(12);
+    for (auto &it : items) buckets[2 * wave_bucket_of(it.Ls) + (e->M[it.h] > 13 * 256 ? 1 : 0)].items.push_back(it);
     const std::vector<int> hrank = model_rank(e);
     for (auto &bk : buckets) {
         if (bk.items.empty()) continue;

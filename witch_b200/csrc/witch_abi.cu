@@ -249,8 +249,10 @@ static std::vector<SClass> s_classes(const witch_ehmm *e, const std::vector<int>
     std::map<std::pair<int, int>, std::vector<int>> m;
     for (int h : hmms) {
         const int M = e->M[h];
-        if (M > 3840) throw std::runtime_error("model longer than 3840 nodes is not supported yet");
-        int C = (M <= 1024) ? 4 : (M <= 3072) ? 8 : 12;
+        if (M > 8192) throw std::runtime_error("model longer than 8192 nodes is not supported");
+        // C = 16 (3,841 .. 8,192 nodes, e.g. the root of a 16S-sized decomposition): the parameter set no longer fits the
+        // register file and spills to local memory -- a slow class for the few models that long, not a fast path
+        int C = (M <= 1024) ? 4 : (M <= 3072) ? 8 : (M <= 3840) ? 12 : 16;
         int T = ((M + C - 1) / C + 31) / 32 * 32;
         if (T < 64) T = 64;
         m[{C, T}].push_back(h);
@@ -317,6 +319,7 @@ static void run_parser(witch_ehmm *e, witch_queries *q, const std::vector<int> &
             case 4: if (T <= 256) launch_parser<4, 256, 2>(e, q, T, wk, st, maxgrid); else launch_parser<4, 512, 1>(e, q, T, wk, st, maxgrid); break;
             case 8: if (T <= 256) launch_parser<8, 256, 2>(e, q, T, wk, st, maxgrid); else launch_parser<8, 384, 1>(e, q, T, wk, st, maxgrid); break;
             case 12: launch_parser<12, 320, 1>(e, q, T, wk, st, maxgrid); break;
+            case 16: launch_parser<16, 512, 1>(e, q, T, wk, st, maxgrid); break;
             default: throw std::runtime_error("bad class");
         }
     }
