@@ -330,7 +330,8 @@ def test_next_rows_at_scale_vs_oracle(wb, tmp_path):
 
 def test_limits_long_queries_and_model_size(wb, tmp_path):
     """Sizes at the edges: queries far longer than any length class boundary (residue staging and scratch are sized per
-    launch), and a model beyond the supported 3,840 nodes must be refused loudly, not mis-scored."""
+    launch), a 6,000-node model runs through the slow parser class, and a model beyond the supported 8,192 nodes must be refused
+    loudly, not mis-scored."""
     import synth
     gold, queries, paths = load_set("dna_small", str(tmp_path))
     rng = np.random.default_rng(9)
