@@ -31,6 +31,7 @@ extern "C" {
 /* flag bits of witch_score's per-pair flags */
 #define WITCH_FLAG_MULTIDOMAIN 1 /* a region failed HMMER's single-domain test (rt3); kept as one envelope */
 #define WITCH_FLAG_SUMSCORE 2    /* the reconstruction ("sum") score overrode the per-sequence score */
+#define WITCH_FLAG_ENVCAP 4      /* more than 6 envelopes were found for the pair; the first 6 were scored */
 
 typedef struct witch_ehmm witch_ehmm;       /* an ensemble of profile HMMs resident on one GPU */
 typedef struct witch_queries witch_queries; /* a digitised, packed query set resident on one GPU */

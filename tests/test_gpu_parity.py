@@ -349,6 +349,18 @@ def test_limits_long_queries_and_model_size(wb, tmp_path):
             assert abs(pre[qi, h] - r["pre_score"]) < SCORE_TOL_BITS
             if r["reported"] and r["nregions"] <= 6:
                 assert abs(sc[qi, h] - r["score"]) < SCORE_TOL_BITS, (qi, h, sc[qi, h], r)
+    # more than 6 envelopes for one pair: the first 6 are scored, WITCH_FLAG_ENVCAP (4) says so
+    hits = gold["hmms"][0]["hits"]
+    best = max(hits, key=lambda n: hits[n]["score"])
+    d0 = hits[best]["domains"][0]
+    seg = dict(queries)[best].upper()[d0[2] - 1:d0[3]][:150]
+    many = "".join(seg + "".join(rng.choice(list("ACGT"), 200)) for _ in range(9))
+    Q9 = wb.Queries(E, [many])
+    sc9, rep9, pre9, fl9 = wb.score(E, Q9)
+    p0 = O.Profile(paths[0])
+    r9 = O.score_pair(p0, p0.abc.digitize(many))
+    assert r9["nregions"] > 6 and abs(pre9[0, 0] - r9["pre_score"]) < SCORE_TOL_BITS
+    assert (fl9[0, 0] & 4) and rep9[0, 0] and np.isfinite(sc9[0, 0])
     cols = wb.align(E, Q, [0, 1], [0, 0])
     prof = O.Profile(paths[0])
     for c, s in zip(cols, [long1, long2]):

@@ -23,7 +23,7 @@ __global__ void finalize_scores_kernel(const PairParse *parse, const int *qlen, 
     const PairParse pp = parse[p];
     const float LN2 = 0.69314718056f;
     const float L = (float)qlen[q];
-    int fl = pp.flags & 1;
+    int fl = pp.flags & 5;   // WITCH_FLAG_MULTIDOMAIN | WITCH_FLAG_ENVCAP
     float score = __int_as_float(0x7fc00000), prev = score;
     uint8_t rep = 0;
     if (qlen[q] > 0) {
