@@ -24,6 +24,8 @@ wl = synth.make_workload("/tmp/witch_b200_bench", **kw)
 rng = np.random.default_rng(0)
 sel = rng.permutation(len(wl["seqs"]))[:nq]
 seqs = [wl["seqs"][i] for i in sel]
+if os.environ.get("PERF_LIB"):
+    _lib.LIB_PATH = os.path.join(ROOT, os.environ["PERF_LIB"])
 lib = _lib.load()
 hp = wl["hmm_paths"]
 if os.environ.get("PERF_SKIP_ROOT"):
