@@ -175,7 +175,10 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser_kernel(DevEhmm E, DevQue
 #pragma unroll
         for (int c = 1; c < C; c++) pDD[c] = pDD[c - 1] * pdd[c];
         float coef[5], Cexcl, Rt, KKl, czl, czl2, Aprev;
-        const int lw = lane & 15;   // cross-warp combinations: both half-warps mirror warps 0..15 (NW <= 16)
+        // cross-warp combinations: lane lw stands for warp lw; every group of CW lanes mirrors warps 0..CW-1 (NW <= CW), so a
+        // log2(CW)-level butterfly finishes them: 3 levels for CTAs of at most 8 warps, 4 otherwise
+        constexpr int CW = (MAXT <= 256) ? 8 : 16;
+        const int lw = lane & (CW - 1);
         {
             float SP = 0.f;
 #pragma unroll
@@ -231,7 +234,7 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser_kernel(DevEhmm E, DevQue
             const float tv = lds_f1v(SA_TOT2(par, lw)), ev = lds_f1v(SA_ES2(par, lw));
             float z = tv * czl, z2 = tv * czl2, et = fmaf(tv, KKl, ev);   // (slots >= NW hold zeros)
 #pragma unroll
-            for (int o = 8; o > 0; o >>= 1) {
+            for (int o = CW / 2; o > 0; o >>= 1) {
                 z += __shfl_xor_sync(0xffffffffu, z, o);
                 z2 += __shfl_xor_sync(0xffffffffu, z2, o);
                 et += __shfl_xor_sync(0xffffffffu, et, o);
@@ -421,7 +424,7 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser_kernel(DevEhmm E, DevQue
             // ---- after it: E_b(i), the scan total, the finished row ----
             float Bi = lds_f1v(SA_ES2(par, lw)), Z = lds_f1v(SA_TOT2(par, lw)) * czl;   // (slots >= NW hold zeros)
 #pragma unroll
-            for (int o = 8; o > 0; o >>= 1) {
+            for (int o = CW / 2; o > 0; o >>= 1) {
                 Bi += __shfl_xor_sync(0xffffffffu, Bi, o);
                 Z += __shfl_xor_sync(0xffffffffu, Z, o);
             }

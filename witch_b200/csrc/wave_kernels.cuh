@@ -338,9 +338,10 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, 
                         acc = fmaf(pm, pa[c], acc); acc = fmaf(pi, pb[c], acc); acc = fmaf(pd, pg[c], acc);
                         nM[c] = acc * e[c];
                     }
-                    nD[0] = fmaf(cM, pmd[0], cD * pdd[0]);
+                    // in-row D chain: the match terms are products off the chain, each link is ONE dependent FFMA
+                    nD[0] = fmaf(cD, pdd[0], cM * pmd[0]);
 #pragma unroll
-                    for (int c = 1; c < C; c++) nD[c] = fmaf(nM[c - 1], pmd[c], nD[c - 1] * pdd[c]);
+                    for (int c = 1; c < C; c++) nD[c] = fmaf(nD[c - 1], pdd[c], nM[c - 1] * pmd[c]);
                     float es = cE;
 #pragma unroll
                     for (int c = 0; c < C; c++) { sM[c] = nM[c]; sI[c] = nI[c]; sD[c] = nD[c]; es += nM[c] + nD[c]; }
@@ -578,7 +579,7 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, 
                         for (int c = C - 1; c >= 0; c--) {
                             const float m1 = (c < C - 1) ? mn[c + 1] : mnR;
                             const float dr = (c < C - 1) ? nD[c + 1] : cDb;
-                            nD[c] = fmaf(m1, oDM[c], fmaf(dr, oDD[c], ebs));
+                            nD[c] = fmaf(dr, oDD[c], fmaf(m1, oDM[c], ebs));   // one dependent FFMA per link of the D chain
                             nM[c] = fmaf(m1, oMM[c], fmaf(sI[c], oMI[c], fmaf(dr, oMD[c], ebs)));
                             nI[c] = fmaf(m1, oIM[c], sI[c] * oII[c]);
                         }
