@@ -55,6 +55,14 @@ static std::vector<WaveBucket> bucketize_items(const witch_ehmm *e, const std::v
 }
 
 // Launches the wavefront kernel over pre-ordered buckets (items of one HMM contiguous); outputs indexed by WaveItem::pair.
+// envelope-mode launch shape: warps per CTA x resident CTAs per SM. 4 x 3 (12 warps/SM, 168 registers) is the measured
+// optimum: 6 x 2 -3 %, 2 x 6 -35 % (six emission tables per SM), 8 x 2 (128 registers, spills) -38 % -- DESIGN.md section 8
+#ifndef WITCH_ENV_WARPS
+#define WITCH_ENV_WARPS 4
+#endif
+#ifndef WITCH_ENV_MINB
+#define WITCH_ENV_MINB 3
+#endif
 template <bool ALIGN, int C, int WAVE_WARPS, int MINB, int RING, bool LANE_EXP>
 static void run_wave_c(witch_ehmm *e, witch_queries *q, std::vector<WaveBucket> &buckets, float *d_envsc, float *d_domcorr,
                      int *d_cols, const long long *d_coloff, float *d_dbg_fwd, float *d_dbg_bwd, cudaStream_t st) {
@@ -121,7 +129,7 @@ static void run_wave(witch_ehmm *e, witch_queries *q, std::vector<WaveBucket> &b
 #define WV_ARGS e, q, buckets, d_envsc, d_domcorr, d_cols, d_coloff, d_dbg_fwd, d_dbg_bwd, st
     const bool lane_exp = e->alph == ALPH_AMINO;  // per-lane scaling exponents (see wave_kernels.cuh)
     if (ALIGN) { if (lane_exp) run_wave_c<true, 8, 4, 2, 3, true>(WV_ARGS); else run_wave_c<true, 8, 4, 2, 3, false>(WV_ARGS); }
-    else { if (lane_exp) run_wave_c<false, 8, 4, 3, 3, true>(WV_ARGS); else run_wave_c<false, 8, 4, 3, 3, false>(WV_ARGS); }
+    else { if (lane_exp) run_wave_c<false, 8, WITCH_ENV_WARPS, WITCH_ENV_MINB, 3, true>(WV_ARGS); else run_wave_c<false, 8, WITCH_ENV_WARPS, WITCH_ENV_MINB, 3, false>(WV_ARGS); }
 #undef WV_ARGS
 }
 
