@@ -58,6 +58,21 @@ constexpr int W_SCALE_EVERY = 8;
 #define WITCH_WAVE_UNROLL_B 2
 #endif
 constexpr int W_UNROLL_F = WITCH_WAVE_UNROLL_F, W_UNROLL_B = WITCH_WAVE_UNROLL_B;
+// Prepared experiments (bit mask, default 0 = the measured round-1 kernel):
+//   1: the lane that issues a TMA copy is chosen with elect.sync instead of `lane == 0` (all operands are warp-uniform);
+//      ptxas then drops the ELECT/R2UR "waterfall" loop it builds around UBLKCP for a possibly divergent issuer
+//   2: the once-per-8-steps exponent-block switch of the Backward step is a real (warp-uniform) branch instead of 16
+//      predicated-off instructions in every step
+//   4: steady-state Backward steps skip the "rows left to request?" test of the Forward-row ring (always true there)
+#ifndef WITCH_WAVE_EXP
+#define WITCH_WAVE_EXP 0
+#endif
+constexpr int W_EXP = WITCH_WAVE_EXP;
+__device__ __forceinline__ bool wave_elect_one() {
+    unsigned p;
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(p));
+    return p != 0;
+}
 __host__ __device__ constexpr int wave_ring_stage_bytes(int C, bool align) { return 32 * C * 4 * (align ? 2 : 1); }
 // ---- TMA (1-D bulk async copy) + mbarrier: completion is tracked in shared memory, not on a register scoreboard
 __device__ __forceinline__ void mbar_init(unsigned bar, int count) {
@@ -191,7 +206,7 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, 
     __syncwarp();
     // boundary records of the neighbouring strip arrive in blocks of 8 rows through a small TMA-fed ring
     auto bnd_issue = [&](const int b) {
-        if (lane == 0) {
+        if ((W_EXP & 1) ? wave_elect_one() : (lane == 0)) {
             mbar_expect_tx(bnd_bar + bq_w * 8, 256);
             tma_load_1d(bnd_ring + bq_w * 256, bnd + 64 * b, 256, bnd_bar + bq_w * 8);
         }
@@ -490,7 +505,7 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, 
             float *tMw = tM + (size_t)(Ls + 31) * 32 * C + lane * 4, *tIw = tI + (size_t)(Ls + 31) * 32 * C + lane * 4;
             int tq_next = 0;   // next step whose rows have not been requested yet
             auto ring_issue = [&]() {
-                if (lane == 0) {
+                if ((W_EXP & 1) ? wave_elect_one() : (lane == 0)) {
                     const unsigned dst = ring_w + wr_stage * RSB, bar = ring_bar + wr_stage * 8;
                     mbar_expect_tx(bar, RSB);
                     tma_load_1d(dst, tMrd, 32 * C * 4, bar);
@@ -549,7 +564,7 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, 
                 const int tF = Ls + 31 - tp;  // forward tile row holding row i of this lane (valid for i >= 1)
                 // keep the ring W_RING-1 steps ahead (tile row 0 exists and is never used), then wait for this step's rows
                 __syncwarp();  // every lane has consumed the stage that is refilled now (it was read one step ago)
-                if (tq_next < nstepsB) ring_issue();
+                if (((W_EXP & 4) && ALL) || tq_next < nstepsB) ring_issue();   // steady state: tq_next <= Ls + 1 < nstepsB always
                 mbar_wait(ring_bar + rd_stage * 8, rd_phase);
                 const unsigned rs = ring_sa + rd_stage * RSB;
                 if (rd_stage == W_RING - 1) { rd_stage = 0; rd_phase ^= 1u; } else rd_stage++;
@@ -626,6 +641,7 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, 
                 }
                 if (ALIGN) { tMw -= 32 * C; tIw -= 32 * C; }
                 if (((tF - 1) & 7) == 0 && tF > 1) {  // next step enters the previous exponent block
+                    if (W_EXP & 2) __syncwarp();   // (not if-convertible: the block becomes a branch taken once per 8 steps)
                     gFc = gFnext;
                     gblk--;
                     gFnext = gFs[GF_AT(max(gblk - 1, 0))];
