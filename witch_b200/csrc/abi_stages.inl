@@ -12,8 +12,6 @@ struct HostClock {   // WITCH_TIMING=1: wall-clock of the host-side phases of a 
     }
 };
 
-static int wave_C_for(const witch_ehmm *) { return 8; }
-
 struct WaveBucket { int Lcap; std::vector<WaveItem> items; };
 
 // Length classes of the wavefront launches (scratch and residue staging are sized by the longest item of a launch).

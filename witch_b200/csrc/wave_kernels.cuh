@@ -148,7 +148,6 @@ template <int C, bool ALIGN, int WAVE_WARPS, int MINB, int W_RING, bool LANE_EXP
 __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, DevQueries Q, WaveWork Wk) {
     extern __shared__ float smem[];
     static_assert(W_RING >= 2, "the Backward sweep reads stored Forward rows through the TMA ring");
-    constexpr bool RING = true;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     __shared__ int s_group;
     __shared__ float s_n2[WAVE_WARPS][MAX_SYM];
