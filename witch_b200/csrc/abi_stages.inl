@@ -113,7 +113,7 @@ static void run_wave_c(witch_ehmm *e, witch_queries *q, std::vector<WaveBucket> 
         wk.dbg_fwd = d_dbg_fwd; wk.dbg_bwd = d_dbg_bwd;
         {
             ScopedTimer tm(ALIGN ? 2 : 1, st, cells);
-            kern<<<(int)grid, WAVE_WARPS * 32, smem, st>>>(e->view(), q->view(), wk);
+            WITCH_LAUNCH(kern, (int)grid, WAVE_WARPS * 32, smem, st)(e->view(), q->view(), wk);
             g_launches++;
             CUDA_TRY(cudaGetLastError());
         }
@@ -187,7 +187,7 @@ extern "C" int witch_score_dev(witch_ehmm *e, witch_queries *q, float *d_scores,
         run_wave<false>(e, q, items, e->f1.p, e->f2.p, nullptr, nullptr, nullptr, nullptr, st);
         hc.lap("run_wave (all buckets)");
         const long long np = (long long)nq * H;
-        finalize_scores_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(e->parse.p, q->dlen.p, nq, H, e->i3.p, e->f1.p,
+        WITCH_LAUNCH(finalize_scores_kernel, (unsigned)((np + 255) / 256), 256, 0, st)(e->parse.p, q->dlen.p, nq, H, e->i3.p, e->f1.p,
                                                                            e->f2.p, d_scores, d_reported, d_pre, d_flags);
         g_launches++;
         CUDA_TRY(cudaGetLastError());
@@ -230,7 +230,7 @@ extern "C" int witch_weights_topk_dev(const witch_ehmm *e, const float *d_scores
         CUDA_TRY(cudaSetDevice(e->device));
         if (nq == 0) return WITCH_OK;
         const int warps = 4;
-        weights_topk_kernel<<<(nq + warps - 1) / warps, warps * 32, 0, (cudaStream_t)stream>>>(
+        WITCH_LAUNCH(weights_topk_kernel, (nq + warps - 1) / warps, warps * 32, 0, (cudaStream_t)stream)(
             d_scores, d_reported, e->dnseq.p, nq, e->H, k, round_decimals, d_idx, d_w, d_count);
         g_launches++;
         CUDA_TRY(cudaGetLastError());
@@ -378,7 +378,7 @@ extern "C" double witch_measure_fp32_peak(double ms_target) {
         double best = 0;
         for (int rep = 0; rep < 6; rep++) {
             CUDA_TRY(cudaEventRecord(a));
-            ffma_peak_kernel<<<grid, block>>>(out.p, iters);
+            WITCH_LAUNCH(ffma_peak_kernel, grid, block)(out.p, iters);
             g_launches++;
             CUDA_TRY(cudaEventRecord(b));
             CUDA_TRY(cudaEventSynchronize(b));
@@ -455,7 +455,7 @@ extern "C" int witch_graph_align(witch_ehmm *e, int nq, const int32_t *qlen, con
         G.pair_w = d_pw.p; G.col_off = d_co.p; G.cols = d_cols.p; G.hmm_off = d_ho.p; G.retained = d_ret.p; G.nongaps = d_ng.p;
         G.backbone_length = backbone_length; G.row_off = d_rowoff.p; G.rows = d_rows.p; G.row_len = d_rl.p;
         G.counter = e->counter.p; G.scratch = scratch.p; G.slot_bytes = slot; G.Lcap = Lcap;
-        graph_dp_kernel<<<(int)grid, 128>>>(G);
+        WITCH_LAUNCH(graph_dp_kernel, (int)grid, 128)(G);
         g_launches++;
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaMemcpy(rows, d_rows.p, (size_t)rows_total, cudaMemcpyDeviceToHost));
@@ -496,10 +496,10 @@ extern "C" int witch_merge_rows(witch_ehmm *e, int nrows, const int64_t *row_off
         W.width = d_w.p; W.gap_start = d_gs.p; W.out = nullptr; W.masked = nullptr; W.out_width = 0;
         const int grid = std::max(1, (nrows + 3) / 4);
         if (nrows > 0) {
-            merge_rows_kernel<false><<<grid, 128>>>(W);
+            WITCH_LAUNCH(merge_rows_kernel<false>, grid, 128)(W);
             g_launches++;
         }
-        merge_scan_kernel<<<1, 1024>>>(d_w.p, B, d_gs.p);
+        WITCH_LAUNCH(merge_scan_kernel, 1, 1024)(d_w.p, B, d_gs.p);
         g_launches++;
         CUDA_TRY(cudaGetLastError());
         long long width_total = 0;
@@ -513,7 +513,7 @@ extern "C" int witch_merge_rows(witch_ehmm *e, int nrows, const int64_t *row_off
         if (masked) d_msk.alloc((size_t)nrows * (size_t)B);
         if (masked) CUDA_TRY(cudaMemset(d_msk.p, '-', (size_t)nrows * (size_t)B));
         W.out = d_out.p; W.masked = masked ? d_msk.p : nullptr; W.out_width = width_total;
-        merge_rows_kernel<true><<<grid, 128>>>(W);
+        WITCH_LAUNCH(merge_rows_kernel<true>, grid, 128)(W);
         g_launches++;
         CUDA_TRY(cudaGetLastError());
         if (merged)

@@ -3,6 +3,13 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+// Kernel launch and dynamic shared memory go through two macros so that the same sources also build as a host-side
+// SIMT simulation (tools/sim: TEST TOOLING, g++ -DWITCH_HOST_SIM; the product library is always the nvcc build).
+#ifndef WITCH_HOST_SIM
+#define WITCH_LAUNCH(kernel, ...) kernel<<<__VA_ARGS__>>>
+#define WITCH_DYN_SMEM(type, name) extern __shared__ type name[]
+#endif
+
 namespace witch {
 
 constexpr int MAX_SYM = 32;   // emission rows a query set may use (Kp of amino is 29)

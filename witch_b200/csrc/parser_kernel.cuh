@@ -62,6 +62,7 @@ __device__ __forceinline__ void load_emis(const float *row, int T, int j, float 
 constexpr int S_RED = 32;  // words per row of the reduction area
 constexpr int PARSER_RED_ROWS = 13;
 
+#ifndef WITCH_HOST_SIM   // (tools/sim/simt.h provides host versions of these helpers)
 // 32-bit shared-memory addressing helpers: keep hot-loop addresses as one pinned register + immediate offsets
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ float4 lds_f4(unsigned a) {
@@ -76,11 +77,12 @@ __device__ __forceinline__ int lds_u8(unsigned a) { unsigned v; asm volatile("ld
 // Opaque identity: stops the compiler from rebuilding a cheap-looking address expression inside the row loop
 #define PIN32(x) asm volatile("" : "+r"(x))
 #define PIN64(x) asm volatile("" : "+l"(x))
+#endif
 constexpr int PARSER_SCRATCH_ROWS = 21;  // floats of scratch per sequence row and CTA
 
 template <int C, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) mh_parser_kernel(DevEhmm E, DevQueries Q, ParserWork Wk) {
-    extern __shared__ float smem[];
+    WITCH_DYN_SMEM(float, smem);
     int T = blockDim.x, tid = threadIdx.x;
     PIN32(T); PIN32(tid);
     int lane = tid & 31, w = tid >> 5, NW = T >> 5;

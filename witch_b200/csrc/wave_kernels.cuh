@@ -68,12 +68,15 @@ constexpr int W_UNROLL_F = WITCH_WAVE_UNROLL_F, W_UNROLL_B = WITCH_WAVE_UNROLL_B
 #define WITCH_WAVE_EXP 0
 #endif
 constexpr int W_EXP = WITCH_WAVE_EXP;
+#ifndef WITCH_HOST_SIM
 __device__ __forceinline__ bool wave_elect_one() {
     unsigned p;
     asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(p));
     return p != 0;
 }
+#endif
 __host__ __device__ constexpr int wave_ring_stage_bytes(int C, bool align) { return 32 * C * 4 * (align ? 2 : 1); }
+#ifndef WITCH_HOST_SIM
 // ---- TMA (1-D bulk async copy) + mbarrier: completion is tracked in shared memory, not on a register scoreboard
 __device__ __forceinline__ void mbar_init(unsigned bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
@@ -95,14 +98,18 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
         "DONE_%=:\n\t}" :: "r"(bar), "r"(parity) : "memory");
 }
 __device__ __forceinline__ int lds_i1v(unsigned a) { int v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+#endif
 constexpr int W_BND_SLOTS = 3;      // ring of 8-row blocks of strip-boundary records (256 B each) per warp
 __host__ __device__ constexpr int wave_bnd_ring_bytes() { return W_BND_SLOTS * (256 + 8); }
+#ifndef WITCH_HOST_SIM
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ float4 lds_f4v(unsigned a) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
     return v;
 }
+#endif
 
 // scratch layout helper (all offsets in bytes, per warp slot)
 struct WaveLayout {
@@ -146,7 +153,7 @@ __device__ __forceinline__ bool oa_e_better(float v2, int d2, int o2, float v1, 
 
 template <int C, bool ALIGN, int WAVE_WARPS, int MINB, int W_RING, bool LANE_EXP>
 __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, DevQueries Q, WaveWork Wk) {
-    extern __shared__ float smem[];
+    WITCH_DYN_SMEM(float, smem);
     static_assert(W_RING >= 2, "the Backward sweep reads stored Forward rows through the TMA ring");
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     __shared__ int s_group;
@@ -200,7 +207,7 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, 
         for (int k = 0; k < W_RING; k++) mbar_init(ring_bar + k * 8, 1);
 #pragma unroll
         for (int k = 0; k < W_BND_SLOTS; k++) mbar_init(bnd_bar + k * 8, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_mbar_init();
     }
     __syncwarp();
     // boundary records of the neighbouring strip arrive in blocks of 8 rows through a small TMA-fed ring

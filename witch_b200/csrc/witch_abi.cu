@@ -266,13 +266,14 @@ template <int C, int MAXT, int MINB>
 static void launch_parser(const witch_ehmm *e, const witch_queries *q, int T, ParserWork wk, cudaStream_t st, int maxgrid) {
     const size_t smem = ((size_t)q->nsym * T * C + PARSER_RED_ROWS * S_RED) * sizeof(float);
     if (smem > 200 * 1024) throw std::runtime_error("emission table does not fit shared memory (too many symbols x model length)");
-    CUDA_TRY(cudaFuncSetAttribute(mh_parser_kernel<C, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = mh_parser_kernel<C, MAXT, MINB>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mh_parser_kernel<C, MAXT, MINB>, T, smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, smem));
     if (occ < 1) throw std::runtime_error("parser kernel cannot be resident (registers/shared memory)");
     const long long nitems = (long long)wk.nh * wk.nq;
     const int grid = (int)std::min<long long>(std::min<long long>(nitems, (long long)e->num_sms * occ), maxgrid);
-    mh_parser_kernel<C, MAXT, MINB><<<grid, T, smem, st>>>(e->view(), q->view(), wk);
+    WITCH_LAUNCH(kern, grid, T, smem, st)(e->view(), q->view(), wk);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
 }
