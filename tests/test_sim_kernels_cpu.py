@@ -13,9 +13,9 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run(args):
+def _run(args, env=None):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sim", "sim_check.py")] + args, capture_output=True,
-                       text=True, timeout=900)
+                       text=True, timeout=900, env=dict(os.environ, **(env or {})))
     assert r.returncode == 0 and "SIM CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
     return r.stdout
 
@@ -39,3 +39,15 @@ def test_simulated_kernels_match_oracle_multi_strip_dna(simlib):
 
 def test_simulated_kernels_match_oracle_amino_lane_exponents(simlib):
     _run([simlib, "amino_small", "3", "2"])          # per-lane scaling exponents (LANE_EXP) and the C = 4 parser class
+
+
+def test_simulated_pair_kernel_matches_oracle():
+    """The experimental two-items-per-warp envelope kernel (WITCH_WAVE_PAIR=1, wave_pair_kernel.cuh; not the default
+    build): pairs of unequal length, nine 128-column strips, composition-biased copies of the queries so that the null2
+    corrections it computes are worth more than a bit (a wrong posterior sum would move the score by far more than the
+    1e-3 bits sim_check.py allows)."""
+    r = subprocess.run(["bash", os.path.join(ROOT, "tools", "sim", "build_sim.sh"), "simpair", "-DWITCH_WAVE_PAIR=1"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = _run(["simpair", "dna_sub8", "3", "1"], env={"SIM_BIAS": "0.5:T"})
+    assert "largest null2 correction" in out

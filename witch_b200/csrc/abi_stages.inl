@@ -121,11 +121,74 @@ static void run_wave_c(witch_ehmm *e, witch_queries *q, std::vector<WaveBucket> 
     }
 }
 
+#if WITCH_WAVE_PAIR
+// Envelope pass with two items per warp (wave_pair_kernel.cuh; build-time option, DNA/RNA alphabets only).
+template <int WAVE_WARPS, int MINB, int RING>
+static void run_wave_pair(witch_ehmm *e, witch_queries *q, std::vector<WaveBucket> &buckets, float *d_envsc, float *d_domcorr,
+                          cudaStream_t st) {
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    const double budget = std::min<double>(64.0e9, 0.5 * (double)(free_b + e->bytes.n));
+    for (auto &bk : buckets) {
+        if (bk.items.empty()) continue;
+        int Lcap = 0, maxM = 0;
+        double cells = 0;
+        for (auto &it : bk.items) {
+            Lcap = std::max(Lcap, it.Ls);
+            maxM = std::max(maxM, e->M[it.h]);
+            cells += (double)it.Ls * e->M[it.h];
+        }
+        const int max_strips = (maxM + WP_SW - 1) / WP_SW;
+        std::vector<int> gfirst, gcount;
+        for (size_t i = 0; i < bk.items.size();) {   // groups of up to 2 x WAVE_WARPS consecutive items of one HMM
+            size_t j = i;
+            while (j < bk.items.size() && bk.items[j].h == bk.items[i].h && j - i < (size_t)(2 * WAVE_WARPS)) j++;
+            gfirst.push_back((int)i); gcount.push_back((int)(j - i));
+            i = j;
+        }
+        const WavePairLayout lay = wave_pair_layout(Lcap, max_strips);
+        const int emis_floats = q->nsym * max_strips * WP_SW;
+        const int res_cap = (Lcap + 1 + 15) / 16 * 16;
+        const size_t smem = (size_t)emis_floats * sizeof(float) + (size_t)WAVE_WARPS * wave_pair_smem_per_warp(RING, res_cap);
+        if (smem > 220 * 1024) throw std::runtime_error("emission table + residue staging do not fit shared memory");
+        auto kern = wave_pair_kernel<WAVE_WARPS, MINB, RING>;
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 1;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WAVE_WARPS * 32, smem));
+        if (occ < 1) throw std::runtime_error("wave pair kernel cannot be resident");
+        long long grid = std::min<long long>((long long)gfirst.size(), (long long)e->num_sms * occ);
+        const long long max_slots = (long long)(budget / (double)lay.total);
+        if (max_slots < WAVE_WARPS) throw std::runtime_error("not enough device memory for the wave scratch");
+        grid = std::max<long long>(1, std::min<long long>(grid, max_slots / WAVE_WARPS));
+        e->bytes.alloc((size_t)grid * WAVE_WARPS * lay.total);
+        DevBuf<WaveItem> ditems; ditems.upload(bk.items, st);
+        DevBuf<int> dgf, dgc; dgf.upload(gfirst, st); dgc.upload(gcount, st);
+        e->counter.alloc(64);
+        CUDA_TRY(cudaMemsetAsync(e->counter.p, 0, sizeof(unsigned), st));
+        WaveWork wk;
+        wk.items = ditems.p; wk.group_first = dgf.p; wk.group_count = dgc.p; wk.ngroups = (int)gfirst.size();
+        wk.counter = e->counter.p; wk.scratch = (char *)e->bytes.p; wk.slot_bytes = lay.total; wk.Lcap = Lcap;
+        wk.max_strips = max_strips; wk.emis_floats = emis_floats; wk.res_cap = res_cap; wk.envsc = d_envsc; wk.domcorr = d_domcorr;
+        wk.cols = nullptr; wk.col_off = nullptr; wk.dbg_fwd = nullptr; wk.dbg_bwd = nullptr;
+        {
+            ScopedTimer tm(1, st, cells);
+            WITCH_LAUNCH(kern, (int)grid, WAVE_WARPS * 32, smem, st)(e->view(), q->view(), wk);
+            g_launches++;
+            CUDA_TRY(cudaGetLastError());
+        }
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+}
+#endif
+
 template <bool ALIGN>
 static void run_wave(witch_ehmm *e, witch_queries *q, std::vector<WaveBucket> &buckets, float *d_envsc, float *d_domcorr,
                      int *d_cols, const long long *d_coloff, float *d_dbg_fwd, float *d_dbg_bwd, cudaStream_t st) {
 #define WV_ARGS e, q, buckets, d_envsc, d_domcorr, d_cols, d_coloff, d_dbg_fwd, d_dbg_bwd, st
     const bool lane_exp = e->alph == ALPH_AMINO;  // per-lane scaling exponents (see wave_kernels.cuh)
+#if WITCH_WAVE_PAIR
+    if (!ALIGN && !lane_exp && !d_dbg_fwd && !d_dbg_bwd) { run_wave_pair<WITCH_PAIR_WARPS, WITCH_PAIR_MINB, 3>(e, q, buckets, d_envsc, d_domcorr, st); return; }
+#endif
     if (ALIGN) { if (lane_exp) run_wave_c<true, 8, 4, 2, 3, true>(WV_ARGS); else run_wave_c<true, 8, 4, 2, 3, false>(WV_ARGS); }
     else { if (lane_exp) run_wave_c<false, 8, WITCH_ENV_WARPS, WITCH_ENV_MINB, 3, true>(WV_ARGS); else run_wave_c<false, 8, WITCH_ENV_WARPS, WITCH_ENV_MINB, 3, false>(WV_ARGS); }
 #undef WV_ARGS

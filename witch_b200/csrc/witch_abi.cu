@@ -17,6 +17,18 @@
 #include "hmm_profile.h"
 #include "parser_kernel.cuh"
 #include "wave_kernels.cuh"
+#ifndef WITCH_WAVE_PAIR
+#define WITCH_WAVE_PAIR 0   // 1: envelope pass with two items per warp and packed f32x2 arithmetic (experimental)
+#endif
+#ifndef WITCH_PAIR_WARPS
+#define WITCH_PAIR_WARPS 4
+#endif
+#ifndef WITCH_PAIR_MINB
+#define WITCH_PAIR_MINB 3
+#endif
+#if WITCH_WAVE_PAIR
+#include "wave_pair_kernel.cuh"
+#endif
 #include "post_kernels.cuh"
 #include "graph_kernel.cuh"
 #include "merge_kernel.cuh"
