@@ -10,13 +10,18 @@ cd "$(dirname "$0")/.."
 case "$1" in
 build)
   for v in 0 1 2 3 4 5 6 7; do bash tools/build_variant.sh exp$v -DWITCH_WAVE_EXP=$v > /dev/null 2>&1 & done; wait
-  ls -la tools/bin/libwitch_exp?.so ;;
+  # the two-items-per-warp envelope kernel (wave_pair_kernel.cuh): 3 / 4 CTAs per SM, with and without the elect.sync issue
+  bash tools/build_variant.sh pair -DWITCH_WAVE_PAIR=1 > /dev/null 2>&1 &
+  bash tools/build_variant.sh pair_e1 -DWITCH_WAVE_PAIR=1 -DWITCH_WAVE_EXP=1 > /dev/null 2>&1 &
+  bash tools/build_variant.sh pair_mb4 -DWITCH_WAVE_PAIR=1 -DWITCH_PAIR_MINB=4 > /dev/null 2>&1 &
+  bash tools/build_variant.sh pair_e7 -DWITCH_WAVE_PAIR=1 -DWITCH_WAVE_EXP=7 > /dev/null 2>&1 & wait
+  ls -la tools/bin/libwitch_exp?.so tools/bin/libwitch_pair*.so ;;
 run)
   mkdir -p gpurun_out
   : > gpurun_out/r2_variants.log
   PERF_LIB=tools/bin/libwitch_exp0.so python tools/gpu_perf_c2.py 640 48 base >> gpurun_out/r2_variants.log 2>&1
-  for v in 1 2 4 7; do
-    PERF_LIB=tools/bin/libwitch_exp$v.so timeout 300 python tools/gpu_perf_c2.py 640 48 exp$v >> gpurun_out/r2_variants.log 2>&1 || echo "exp$v FAILED rc=$?" >> gpurun_out/r2_variants.log
+  for v in exp1 exp2 exp4 exp7 pair pair_e1 pair_mb4 pair_e7; do
+    PERF_LIB=tools/bin/libwitch_$v.so timeout 300 python tools/gpu_perf_c2.py 640 48 $v >> gpurun_out/r2_variants.log 2>&1 || echo "$v FAILED rc=$?" >> gpurun_out/r2_variants.log
   done
   cat gpurun_out/r2_variants.log ;;
 *) echo "usage: $0 build|run"; exit 2 ;;

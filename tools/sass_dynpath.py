@@ -29,7 +29,17 @@ def walk(ins, lo, hi, markers):
             cond = t.startswith("@")
             if lo <= ta <= hi and ta > a:
                 region = " ; ".join(x for _, x in ins[i + 1:idx[ta]])
-                if not cond or any(mk in region for mk in markers):
+                rare = any(mk in region for mk in markers)
+                if rare and cond:   # skip only the INNERMOST conditional region that holds a marker
+                    for j in range(i + 1, idx[ta]):
+                        a2, t2 = ins[j]
+                        m2 = re.search(r"\bBRA(?:\.\w+)*\s+(?:!?U?P\w+,\s*)?0x([0-9a-f]+)", t2)
+                        if m2 and t2.startswith("@") and "BRA.DIV" not in t2:
+                            tb = int(m2.group(1), 16)
+                            if a2 < tb <= ta and any(mk in " ; ".join(x for _, x in ins[j + 1:idx[tb]]) for mk in markers):
+                                rare = False
+                                break
+                if not cond or rare:
                     i = idx[ta]
                     continue
         i += 1

@@ -52,7 +52,7 @@ __host__ __device__ inline WavePairLayout wave_pair_layout(int Lcap, int max_str
     return w;
 }
 __host__ __device__ constexpr int wave_pair_smem_per_warp(int ring, int res_cap) {
-    return 2 * res_cap + ring * (WP_STAGE + 8) + W_BND_SLOTS * (WP_BND_BLK + 8);
+    return 2 * res_cap + ring * (WP_STAGE + 8) + W_BND_SLOTS * (WP_BND_BLK + 8) + WP_BND_REC * 4;   // + one all-zero record
 }
 
 template <int WAVE_WARPS, int MINB, int W_RING>
@@ -82,11 +82,15 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_pair_kernel(DevEhm
     unsigned bq_ph = 0;
     // dynamic shared memory after the emission table: residues (2 per warp) | Forward-row ring | its mbarriers | boundary ring | its mbarriers
     const unsigned sm_dyn = emis_sa + Wk.emis_floats * 4;
-    const unsigned ring_w = sm_dyn + WAVE_WARPS * 2 * Wk.res_cap + w * (W_RING * WP_STAGE);
-    const unsigned ring_sa = ring_w + lane * 16;   // stage layout [quad v][lane][4 floats]: conflict-free LDS.128
-    const unsigned ring_bar = sm_dyn + WAVE_WARPS * 2 * Wk.res_cap + WAVE_WARPS * (W_RING * WP_STAGE) + w * (W_RING * 8);
-    const unsigned bnd_ring = sm_dyn + WAVE_WARPS * 2 * Wk.res_cap + WAVE_WARPS * (W_RING * (WP_STAGE + 8)) + w * (W_BND_SLOTS * WP_BND_BLK);
-    const unsigned bnd_bar = sm_dyn + WAVE_WARPS * 2 * Wk.res_cap + WAVE_WARPS * (W_RING * (WP_STAGE + 8) + W_BND_SLOTS * WP_BND_BLK) + w * (W_BND_SLOTS * 8);
+    unsigned ring_w = sm_dyn + WAVE_WARPS * 2 * Wk.res_cap + w * (W_RING * WP_STAGE);
+    unsigned ring_sa = ring_w + lane * 16;   // stage layout [quad v][lane][4 floats]: conflict-free LDS.128
+    unsigned ring_bar = sm_dyn + WAVE_WARPS * 2 * Wk.res_cap + WAVE_WARPS * (W_RING * WP_STAGE) + w * (W_RING * 8);
+    unsigned bnd_ring = sm_dyn + WAVE_WARPS * 2 * Wk.res_cap + WAVE_WARPS * (W_RING * (WP_STAGE + 8)) + w * (W_BND_SLOTS * WP_BND_BLK);
+    unsigned bnd_bar = sm_dyn + WAVE_WARPS * 2 * Wk.res_cap + WAVE_WARPS * (W_RING * (WP_STAGE + 8) + W_BND_SLOTS * WP_BND_BLK) + w * (W_BND_SLOTS * 8);
+    // an all-zero boundary record: what the first strip (Forward) / the last strip (Backward) reads instead of a neighbour's
+    unsigned zrec = sm_dyn + WAVE_WARPS * 2 * Wk.res_cap + WAVE_WARPS * (W_RING * (WP_STAGE + 8) + W_BND_SLOTS * (WP_BND_BLK + 8)) + w * (WP_BND_REC * 4);
+    PIN32(ring_w); PIN32(ring_sa); PIN32(ring_bar); PIN32(bnd_ring); PIN32(bnd_bar); PIN32(zrec);   // one register each, no re-derivation in the loops
+    if (lane < WP_BND_REC) sts_f1(zrec + lane * 4, 0.f);
     if (lane == 0) {
 #pragma unroll
         for (int k = 0; k < W_RING; k++) mbar_init(ring_bar + k * 8, 1);
@@ -96,7 +100,7 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_pair_kernel(DevEhm
     }
     __syncwarp();
     auto bnd_issue = [&](const int b) {   // block b = records of rows 8b .. 8b+7
-        if (lane == 0) {
+        if ((W_EXP & 1) ? wave_elect_one() : (lane == 0)) {
             mbar_expect_tx(bnd_bar + bq_w * 8, WP_BND_BLK);
             tma_load_1d(bnd_ring + bq_w * WP_BND_BLK, bnd + 8 * WP_BND_REC * b, WP_BND_BLK, bnd_bar + bq_w * 8);
         }
@@ -136,7 +140,8 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_pair_kernel(DevEhm
         const int Ls = max(Ls2.x, Ls2.y);
         const int dL = Ls - min(Ls2.x, Ls2.y);
         // residues of both items in shared memory, the shorter one padded with its last residue up to Ls
-        const unsigned sresA = emis_sa + Wk.emis_floats * 4 + (2 * w) * Wk.res_cap, sresB = sresA + Wk.res_cap;
+        unsigned sresA = emis_sa + Wk.emis_floats * 4 + (2 * w) * Wk.res_cap, sresB = sresA + Wk.res_cap;
+        PIN32(sresA); PIN32(sresB);
         {
             uint8_t *sr = reinterpret_cast<uint8_t *>(emis_s + Wk.emis_floats) + (2 * w) * Wk.res_cap;
             const uint8_t *da = Q.dsq + Q.off[itA.q] + (itA.i0 - 1), *db = Q.dsq + Q.off[itB.q] + (itB.i0 - 1);
@@ -150,7 +155,8 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_pair_kernel(DevEhm
         const float2 pmove = p_mk(2.0f / ((float)Q.len[itA.q] + 2.0f), 2.0f / ((float)Q.len[itB.q] + 2.0f));
         const float2 ploop = p_mk(1.0f - pmove.x, 1.0f - pmove.y);
         const int nsteps = Ls + 31;
-        const unsigned erow = Mstr * 4;
+        unsigned erow = Mstr * 4;
+        PIN32(erow);
 
         // ======================================= Forward =======================================
         float2 xCv = p_dup(0.f), xCfin = p_dup(0.f);
@@ -196,6 +202,7 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_pair_kernel(DevEhm
             unsigned ebase = emis_sa + (s * SW + lane * C) * 4;
             float *tMp = tile + (size_t)s * TT * (SW * 2) + (SW * 2) + lane * 4;   // (step 1, quad 0, lane); step = [v][lane][4]
             int *gFs = gFarr + s * TG * 2;
+            PIN32(ebase); PIN64(tMp); PIN64(gFs);
             if (last) { xCv = p_dup(0.f); xCg = g; }
             int xa = lds_u8(sresA + min(max(-lane, 0), Ls - 1)), xb = lds_u8(sresB + min(max(-lane, 0), Ls - 1));
             int bcur = 0;
@@ -210,30 +217,33 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_pair_kernel(DevEhm
                 bnd_wait();
                 if (bmax >= 1) bnd_wait();
             }
-            auto fstep = [&](const int t, auto allc) {
+            auto fstep = [&](const int t, auto allc, auto uc) {
                 constexpr bool ALL = decltype(allc)::value;
+                constexpr int U = decltype(uc)::value;   // steady state: t = 8j + 1 + U, so t & 7 is a compile-time constant
                 const int i = t - lane;
                 const bool act = ALL || (i >= 1 && i <= Ls);
                 float2 cM = p_up(sM[C - 1]), cI = p_up(sI[C - 1]), cD = p_up(sD[C - 1]), cE = p_up(ep);
-                {   // lane 0: strip boundary of the left strip, or zeros; branch-free
-                    float2 f = p_dup(0.f);
-                    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+                {   // lane 0: strip boundary of the left strip (first strip: the all-zero record); scalar, predicated
+                    unsigned ra = zrec;
                     if (s > 0) {
                         const int tr = ALL ? t : min(t, Ls);
-                        if ((t & 7) == 0 && (ALL || t <= Ls)) {   // row t opens boundary block t >> 3
+                        const int t7 = ALL ? ((1 + U) & 7) : (t & 7), tr7 = ALL ? ((1 + U) & 7) : (tr & 7);
+                        if (t7 == 0 && (ALL || t <= Ls)) {   // row t opens boundary block t >> 3
                             const int b = t >> 3;
                             __syncwarp();
                             if (8 * (b + 2) <= Ls) bnd_issue(b + 2);
                             if (8 * (b + 1) <= Ls) bnd_wait();
                             bcur = bnd_next(bcur);
                         }
-                        const unsigned ra = bnd_ring + bcur * WP_BND_BLK + (tr & 7) * (WP_BND_REC * 4);
-                        r0 = lds_f4v(ra); r1 = lds_f4v(ra + 16);
-                        if (act) f = p_mk(pow2i(lds_i1v(ra + 32) - g.x), pow2i(lds_i1v(ra + 36) - g.y));
+                        ra = bnd_ring + bcur * WP_BND_BLK + tr7 * (WP_BND_REC * 4);
                     }
-                    const float2 bM = p_mul(p_mk(r0.x, r0.y), f), bI = p_mul(p_mk(r0.z, r0.w), f);
-                    const float2 bD = p_mul(p_mk(r1.x, r1.y), f), bE = p_mul(p_mk(r1.z, r1.w), f);
-                    cM = p_sel(lane == 0, bM, cM); cI = p_sel(lane == 0, bI, cI); cD = p_sel(lane == 0, bD, cD); cE = p_sel(lane == 0, bE, cE);
+                    const float4 r0 = lds_f4v(ra), r1 = lds_f4v(ra + 16);
+                    float fx = pow2i(lds_i1v(ra + 32) - g.x), fy = pow2i(lds_i1v(ra + 36) - g.y);
+                    if (!ALL && !act) { fx = 0.f; fy = 0.f; }
+                    if (lane == 0) {
+                        cM.x = r0.x * fx; cM.y = r0.y * fy; cI.x = r0.z * fx; cI.y = r0.w * fy;
+                        cD.x = r1.x * fx; cD.y = r1.y * fy; cE.x = r1.z * fx; cE.y = r1.w * fy;
+                    }
                 }
                 const int xra = xa, xrb = xb;
                 {
@@ -312,20 +322,23 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_pair_kernel(DevEhm
                 const std::integral_constant<bool, false> genc;
                 const std::integral_constant<bool, true> allc;
                 int t = 1;
+                const std::integral_constant<int, -1> nou;
                 for (; t <= 32; t++) {
                     if (((t - 1) & 7) == 0) fmark(t);
-                    fstep(t, genc);
+                    fstep(t, genc, nou);
                     if ((t & (W_SCALE_EVERY - 1)) == 0) frescale(t);
                 }
-                for (; t + 7 <= Ls; t += 8) {
+                for (; t + 7 <= Ls; t += 8) {   // t = 33, 41, ...
                     fmark(t);
-#pragma unroll
-                    for (int u = 0; u < 8; u++) fstep(t + u, allc);
+                    fstep(t, allc, std::integral_constant<int, 0>()); fstep(t + 1, allc, std::integral_constant<int, 1>());
+                    fstep(t + 2, allc, std::integral_constant<int, 2>()); fstep(t + 3, allc, std::integral_constant<int, 3>());
+                    fstep(t + 4, allc, std::integral_constant<int, 4>()); fstep(t + 5, allc, std::integral_constant<int, 5>());
+                    fstep(t + 6, allc, std::integral_constant<int, 6>()); fstep(t + 7, allc, std::integral_constant<int, 7>());
                     frescale(t + 7);
                 }
                 for (; t <= nsteps; t++) {
                     if (((t - 1) & 7) == 0) fmark(t);
-                    fstep(t, genc);
+                    fstep(t, genc, nou);
                     if ((t & (W_SCALE_EVERY - 1)) == 0) frescale(t);
                 }
             }
@@ -388,6 +401,7 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_pair_kernel(DevEhm
             const bool hasR = !(lastS && lane == 31);
             float *tM = tile + (size_t)s * TT * (SW * 2);
             const int *gFs = gFarr + s * TG * 2;
+            PIN32(ebase); PIN64(gFs);
             int bcur = 0;
             int gblk = (Ls + 30) >> 3;
             PairI gFc = {gFs[2 * gblk], gFs[2 * gblk + 1]};
@@ -398,9 +412,10 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_pair_kernel(DevEhm
             float2 fac = post_scale(gFc, g);
             int xa = lds_u8(sresA + Ls - 1), xb = lds_u8(sresB + Ls - 1);   // residue i+1 of the lane's row at the next step
             const float *tMrd = tM + (size_t)(Ls + 31) * (SW * 2);   // rows of step 0; step tq is SW*2 floats earlier
+            PIN64(tMrd);
             int tq_next = 0;
             auto ring_issue = [&]() {
-                if (lane == 0) {
+                if ((W_EXP & 1) ? wave_elect_one() : (lane == 0)) {
                     const unsigned dst = ring_w + wr_stage * WP_STAGE, bar = ring_bar + wr_stage * 8;
                     mbar_expect_tx(bar, WP_STAGE);
                     tma_load_1d(dst, tMrd, WP_STAGE, bar);
@@ -427,9 +442,8 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_pair_kernel(DevEhm
                 const int i = Ls - (tp - (31 - lane));
                 const bool act = ALL || (i >= 0 && i <= Ls);
                 float2 cMb = p_down(sM[0]), cDb = p_down(sD[0]), cB = p_down(bp);
-                {   // lane 31: boundary of the strip to the right, or zeros; branch-free
-                    float2 f = p_dup(0.f);
-                    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+                {   // lane 31: boundary of the strip to the right (last strip: the all-zero record); scalar, predicated
+                    unsigned ra = zrec;
                     if (!lastS) {
                         const int i31 = ALL ? Ls - tp : max(Ls - tp, 0);
                         if ((i31 & 7) == 7 && tp > 0 && (ALL || tp <= Ls)) {
@@ -439,12 +453,14 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_pair_kernel(DevEhm
                             if (b >= 1) bnd_wait();
                             bcur = bnd_next(bcur);
                         }
-                        const unsigned ra = bnd_ring + bcur * WP_BND_BLK + (i31 & 7) * (WP_BND_REC * 4);
-                        r0 = lds_f4v(ra); r1 = lds_f4v(ra + 16);
-                        if (act) f = p_mk(pow2i(lds_i1v(ra + 32) - g.x), pow2i(lds_i1v(ra + 36) - g.y));
+                        ra = bnd_ring + bcur * WP_BND_BLK + (i31 & 7) * (WP_BND_REC * 4);
                     }
-                    const float2 bM = p_mul(p_mk(r0.x, r0.y), f), bD = p_mul(p_mk(r1.x, r1.y), f), bB = p_mul(p_mk(r1.z, r1.w), f);
-                    cMb = p_sel(lane == 31, bM, cMb); cDb = p_sel(lane == 31, bD, cDb); cB = p_sel(lane == 31, bB, cB);
+                    const float4 r0 = lds_f4v(ra), r1 = lds_f4v(ra + 16);
+                    float fx = pow2i(lds_i1v(ra + 32) - g.x), fy = pow2i(lds_i1v(ra + 36) - g.y);
+                    if (!ALL && !act) { fx = 0.f; fy = 0.f; }
+                    if (lane == 31) {
+                        cMb.x = r0.x * fx; cMb.y = r0.y * fy; cDb.x = r1.x * fx; cDb.y = r1.y * fy; cB.x = r1.z * fx; cB.y = r1.w * fy;
+                    }
                 }
                 __syncwarp();
                 if (ALL || tq_next < nstepsB) ring_issue();
