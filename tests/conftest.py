@@ -18,7 +18,7 @@ def pytest_collection_modifyitems(config, items):
         has_gpu = torch.cuda.is_available()
     except Exception:
         has_gpu = False
-    if has_gpu:
+    if has_gpu or os.environ.get("WITCH_SIM_DRYRUN") == "1":   # (tools/sim/run_gpu_tests_in_sim.py: developer dry run)
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:
