@@ -68,3 +68,16 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".inl")):
                 src = open(os.path.join(dp, f)).read()
                 assert "oracle" not in src.replace("Oracle", ""), f
+
+
+def test_product_never_loads_the_simulation_build():
+    """tools/sim (host SIMT simulation of the kernels) is developer/test tooling: the package must not know its library,
+    and the only path the binding loads by default is the nvcc-built libwitch_b200.so."""
+    pkg = os.path.join(ROOT, "witch_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert "libwitch_sim" not in src and "tools/sim" not in src and "WITCH_HOST_SIM" not in src, f
+    from witch_b200 import _lib
+    assert _lib.LIB_PATH == os.path.join(pkg, "csrc", "libwitch_b200.so")
