@@ -1,7 +1,33 @@
 // Fiber scheduler of the host SIMT simulation (tools/sim/simt.h). TEST TOOLING ONLY.
 #include "simt.h"
 
+#ifdef SIMT_FAST_SWITCH
+asm(R"(
+.text
+.globl simt_swap
+.type simt_swap,@function
+simt_swap:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size simt_swap,.-simt_swap
+)");
+#endif
+
 namespace simt {
+void *g_sched_sp = nullptr;
 Block *g_blk = nullptr;
 Fiber *g_cur = nullptr;
 ucontext_t g_sched;
@@ -21,7 +47,12 @@ static void fiber_main() {
     w.live--; b.live--;
     if (w.live > 0 && w.count >= w.live) { w.count = 0; w.gen = w.gen + 1; }
     if (b.live > 0 && b.bar_count >= b.live) { b.bar_count = 0; b.bar_gen = b.bar_gen + 1; }
+#ifdef SIMT_FAST_SWITCH
+    simt_swap(&f->sp, g_sched_sp);
+    abort();   // a finished fiber is never resumed
+#else
     swapcontext(&f->ctx, &g_sched);
+#endif
 }
 
 void run_grid(unsigned grid, unsigned block, const std::function<void()> &body) {
@@ -41,11 +72,22 @@ void run_grid(unsigned grid, unsigned block, const std::function<void()> &body) 
         for (unsigned t = 0; t < block; t++) {
             Fiber &f = b.fibers[t];
             f.tIdx = uint3{t, 0, 0};
+#ifdef SIMT_FAST_SWITCH
+            {   // initial frame: six callee-saved slots, then the entry point as the return address of simt_swap
+                uintptr_t top = ((uintptr_t)stacks[t] + STACK) & ~(uintptr_t)15;
+                void **sp = (void **)top;
+                *--sp = nullptr;                  // fake return address of fiber_main (never used)
+                *--sp = (void *)&fiber_main;
+                for (int k = 0; k < 6; k++) *--sp = nullptr;
+                f.sp = sp;
+            }
+#else
             getcontext(&f.ctx);
             f.ctx.uc_stack.ss_sp = stacks[t];
             f.ctx.uc_stack.ss_size = STACK;
             f.ctx.uc_link = &g_sched;
             makecontext(&f.ctx, fiber_main, 0);
+#endif
         }
         int remaining = (int)block;
         while (remaining > 0) {
@@ -55,7 +97,11 @@ void run_grid(unsigned grid, unsigned block, const std::function<void()> &body) 
                 if (f.done) continue;
                 if (f.wait_ptr && *f.wait_ptr == f.wait_val) continue;
                 g_cur = &f;
+#ifdef SIMT_FAST_SWITCH
+                simt_swap(&g_sched_sp, f.sp);
+#else
                 swapcontext(&g_sched, &f.ctx);
+#endif
                 progressed = true;
                 if (f.done) remaining--;
             }

@@ -44,8 +44,13 @@ template <class A, class B> static inline auto min(A a, B b) -> decltype(a + b) 
 template <class A, class B> static inline auto max(A a, B b) -> decltype(a + b) { return a > b ? a : b; }
 
 namespace simt {
+#if defined(__x86_64__) && !defined(SIMT_USE_UCONTEXT)
+#define SIMT_FAST_SWITCH 1   // hand-written context switch (callee-saved registers + stack pointer): no sigprocmask system calls
+extern "C" void simt_swap(void **save_sp, void *load_sp);
+#endif
 struct Fiber {
     ucontext_t ctx;
+    void *sp = nullptr;
     char *stack = nullptr;
     uint3 tIdx{0, 0, 0};
     bool done = false;
@@ -62,11 +67,16 @@ struct Block {
 extern Block *g_blk;
 extern Fiber *g_cur;
 extern ucontext_t g_sched;
+extern void *g_sched_sp;
 extern uint3 g_blockIdx, g_blockDim, g_gridDim;
 extern char g_smem_arena[];
 extern unsigned long long g_switches;
 void run_grid(unsigned grid, unsigned block, const std::function<void()> &body);
+#ifdef SIMT_FAST_SWITCH
+inline void yield() { g_switches++; simt_swap(&g_cur->sp, g_sched_sp); }
+#else
 inline void yield() { g_switches++; swapcontext(&g_cur->ctx, &g_sched); }
+#endif
 inline void wait_change(volatile unsigned *p, unsigned seen) {
     g_cur->wait_ptr = p; g_cur->wait_val = seen;
     while (*p == seen) yield();
