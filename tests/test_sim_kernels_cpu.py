@@ -51,3 +51,14 @@ def test_simulated_pair_kernel_matches_oracle():
     assert r.returncode == 0, r.stderr[-3000:]
     out = _run(["simpair", "dna_sub8", "3", "1"], env={"SIM_BIAS": "0.5:T"})
     assert "largest null2 correction" in out
+
+
+def test_gpu_parity_tests_dry_run_in_simulation(simlib):
+    """The GPU-marked parity tests themselves (tests/test_gpu_parity.py), executed against the simulation build: the full
+    dna_small and amino_small golden sets (reported sets, 0.01-bit scores, hmmsearch's printed scores, weights, hmmalign's
+    columns), the edge cases, the mirror interface, the graph-DP rows and the merged alignment of the reference's Python.
+    A dry run of the test logic and of the kernels' arithmetic -- the parity claim itself is the same tests on a B200."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sim", "run_gpu_tests_in_sim.py"), simlib,
+                        "scores_weights_columns and (dna_small or amino_small) or edge_cases or mirror_interface or "
+                        "merge_matches or graph_dp_matches"], capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0 and "6 passed" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
