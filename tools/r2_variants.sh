@@ -23,6 +23,9 @@ run)
   for v in exp1 exp2 exp4 exp7 pair pair_e1 pair_mb4 pair_e7; do
     PERF_LIB=tools/bin/libwitch_$v.so timeout 300 python tools/gpu_perf_c2.py 640 48 $v >> gpurun_out/r2_variants.log 2>&1 || echo "$v FAILED rc=$?" >> gpurun_out/r2_variants.log
   done
+  # full GPU parity tests against the pair kernel (the default library is covered by `pytest -m gpu` itself)
+  timeout 900 python tools/run_tests_with_lib.py tools/bin/libwitch_pair.so > gpurun_out/r2_pair_pytest.log 2>&1 || echo "pair parity tests FAILED" >> gpurun_out/r2_variants.log
+  tail -n 3 gpurun_out/r2_pair_pytest.log >> gpurun_out/r2_variants.log
   cat gpurun_out/r2_variants.log ;;
 *) echo "usage: $0 build|run"; exit 2 ;;
 esac
