@@ -61,8 +61,36 @@ def _gloo_worker(rank, world, port, q):
         cnt = np.zeros(len(mine), np.int32)
         for j, qq in enumerate(mine):  # fake per-query records that encode the global query id
             idx[j, 0] = qq; w[j, 0] = qq / 1000.0; cnt[j] = 1
-        gi, gw, gc = sharding.gather_topk(idx, w, cnt, mine, n, device="cpu")
-        ok = bool((gi[:, 0] == np.arange(n)).all() and np.allclose(gw[:, 0], np.arange(n) / 1000.0) and (gc == 1).all())
+        gi, gw, gc = [t.numpy() for t in sharding.gather_topk(idx, w, cnt, mine, n, device="cpu")]
+        ok = bool((gi[:, 0] == np.arange(n)).all() and np.allclose(gw[:, 0], np.arange(n) / 1000.0) and (gc == 1).all()
+                  and (gi[:, 1:] == -1).all())
+        # the sharded driver end to end with stand-ins for the device objects: every rank uploads exactly its own
+        # queries' residues and ends with the same global table
+        import ctypes
+        import torch
+        rng = np.random.default_rng(3)
+        lens = rng.integers(1, 40, 57)
+        off = np.zeros(len(lens) + 1, dtype=np.int64); np.cumsum(lens, out=off[1:])
+        blob = rng.integers(65, 90, int(off[-1])).astype(np.uint8)
+
+        class FakeQ:
+            def __init__(self, ehmm, ptr, offsets):
+                src = (ctypes.c_char * int(offsets[-1])).from_address(int(ptr))
+                self.res = np.frombuffer(src, dtype=np.uint8).copy(); self.off = np.asarray(offsets); self.n = len(offsets) - 1
+
+        class FakePipe:
+            ehmm = None; device = torch.device("cpu"); k = 3
+
+            def run(self, qq):   # record = (sum of residues, length) of each uploaded query
+                sums = np.array([qq.res[qq.off[j]:qq.off[j + 1]].sum() for j in range(qq.n)], dtype=np.int32)
+                idx = np.full((qq.n, 3), -1, np.int32); idx[:, 0] = sums
+                w = np.zeros((qq.n, 3)); w[:, 0] = np.diff(qq.off)
+                return dict(idx=torch.as_tensor(idx), w=torch.as_tensor(w), count=torch.ones(qq.n, dtype=torch.int32))
+
+        out = sharding.run_sharded(FakePipe(), blob.ctypes.data, off, rank, world, queries_factory=FakeQ)
+        want = np.array([blob[off[j]:off[j + 1]].sum() for j in range(len(lens))])
+        ok = ok and bool((out["idx"][:, 0].numpy() == want).all() and (out["w"][:, 0].numpy() == lens).all()
+                         and len(out["mine"]) in (28, 29) and out["queries"].n == len(out["mine"]))
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()

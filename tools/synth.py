@@ -6,13 +6,16 @@ Bench/test tooling, not product code. Generates:
   * a backbone (full-length leaves) + its true alignment, queries (full length and/or fragments),
   * the eHMM: hierarchical centroid bisection of the backbone tree down to <= `decomp` leaves
     (reference behaviour: witch_msa/gcmm/tree.py:384-438 keeps every subtree, 1+2+4+... subsets),
-  * one HMMER3/f text profile per subset. Profiles are estimated here with a simple pseudocount estimator
-    (every non-all-gap column is a match state, as `--symfrac 0.0` does in gcmm/algorithm.py:463-470) -- the
-    reference's hmmbuild is out of scope for the hot path; both the CUDA path and the reference CPU binaries
-    read these same files.
+  * one HMMER3/f text profile per subset, built by the reference's own `hmmbuild` with WITCH's command line
+    (`--cpu 1 --dna|--amino --ere 0.59 --symfrac 0.0 --informat afa`, gcmm/algorithm.py:463-470) when the staged
+    binary oracle/_ref/hmmer/hmmbuild is present (meta["profiles"] == "hmmbuild"). Fallback, stated in
+    meta["profiles"] == "pseudocount": a simple pseudocount estimator (every non-all-gap column is a match state,
+    as `--symfrac 0.0` does). Both the CUDA path and the reference CPU binaries read these same files.
 """
 import hashlib
 import os
+import subprocess
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -176,12 +179,48 @@ def write_hmm(path, name, counts, trans_counts, nseq, alphabet):
         f.write("\n".join(lines) + "\n")
 
 
+HMMBUILD = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "hmmer", "hmmbuild")
+
+
+def _hmmbuild_leng(path):
+    try:
+        with open(path) as f:
+            for ln in f:
+                if ln.startswith("LENG"):
+                    return int(ln.split()[1])
+                if ln.startswith("HMM "):
+                    break
+    except OSError:
+        pass
+    return -1
+
+
+def _run_hmmbuild(job):
+    """One subset: write hmmbuild.input.<label>.fasta (the subset alignment, all-gap columns removed) and run the
+    reference's hmmbuild with WITCH's flags (gcmm/algorithm.py:463-470). -> True when the profile has one match state
+    per retained column."""
+    hmm_path, aln_path, rows, lut, molecule, ncols = job
+    if _hmmbuild_leng(hmm_path) == ncols:
+        return True
+    with open(aln_path, "w") as f:
+        for r in range(rows.shape[0]):
+            f.write(">s%d\n%s\n" % (r, "".join(lut[rows[r]])))
+    subprocess.run([HMMBUILD, "--cpu", "1", "--" + molecule, "--ere", "0.59", "--symfrac", "0.0", "--informat", "afa",
+                    "-o", "/dev/null", hmm_path, aln_path], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    os.remove(aln_path)
+    return _hmmbuild_leng(hmm_path) == ncols
+
+
 def make_workload(outdir, alphabet="dna", n_total=10000, n_backbone=1000, root_len=1550, decomp=10, frag_frac=0.25,
-                  frag_mean=400, seed=1, n_queries=None, max_hmms=None, mean_blen=0.02, indel_rate=0.0065):
+                  frag_mean=400, seed=1, n_queries=None, max_hmms=None, mean_blen=0.02, indel_rate=0.0065,
+                  profiles="auto"):
     """Build (or reuse) a workload directory. Returns dict(hmm_paths, nseq, names, seqs, retained_columns,
-    nongaps_per_column, backbone_length, meta)."""
+    nongaps_per_column, backbone_length, meta). profiles: "hmmbuild" (the reference binary), "pseudocount" (the
+    built-in estimator) or "auto" (hmmbuild when oracle/_ref is staged)."""
+    if profiles == "auto":
+        profiles = "hmmbuild" if os.access(HMMBUILD, os.X_OK) else "pseudocount"
     key = hashlib.sha1(repr((alphabet, n_total, n_backbone, root_len, decomp, frag_frac, frag_mean, seed, n_queries,
-                             max_hmms, mean_blen, indel_rate, "v5")).encode()).hexdigest()[:12]
+                             max_hmms, mean_blen, indel_rate, "v6", profiles)).encode()).hexdigest()[:12]
     wd = os.path.join(outdir, "synth_" + key)
     abc = DNA if alphabet == "dna" else AMINO
     K = len(abc)
@@ -206,7 +245,7 @@ def make_workload(outdir, alphabet="dna", n_total=10000, n_backbone=1000, root_l
         subsets = subsets[:max_hmms]
     row_of = {int(i): r for r, i in enumerate(bb)}
     os.makedirs(wd, exist_ok=True)
-    hmm_paths, nseqs, retained, nongaps = [], [], [], []
+    hmm_paths, nseqs, retained, nongaps, jobs = [], [], [], [], []
     for si, leaves in enumerate(subsets):
         rows = bb_rows[[row_of[i] for i in leaves]]
         present = rows >= 0
@@ -224,10 +263,18 @@ def make_workload(outdir, alphabet="dna", n_total=10000, n_backbone=1000, root_l
         tcn[0, 0] = pres[:, 0].sum(); tcn[0, 1] = (~pres[:, 0]).sum()
         tcn[-1, 0] = pres[:, -1].sum(); tcn[-1, 2] = (~pres[:, -1]).sum()
         p = os.path.join(wd, "hmmbuild.model.A_0_%d" % si)
-        if not os.path.exists(p):
+        if profiles == "hmmbuild":
+            jobs.append((p, os.path.join(wd, "hmmbuild.input.A_0_%d.fasta" % si), sub, np.array(list(abc + "-")),
+                         "dna" if alphabet == "dna" else "amino", len(cols)))
+        elif not os.path.exists(p):
             write_hmm(p, "A_0_%d" % si, counts, tcn, len(leaves), abc)
         hmm_paths.append(p); nseqs.append(len(leaves))
         retained.append(cols.astype(np.int32)); nongaps.append(pres.sum(0).astype(np.int32))
+    if jobs:
+        with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as ex:
+            ok = list(ex.map(_run_hmmbuild, jobs))
+        if not all(ok):
+            raise RuntimeError("hmmbuild did not produce one match state per retained column for %d subsets" % ok.count(False))
     names, seqs = [], []
     lut = np.array(list(abc))
     for n, i in enumerate(qs):
@@ -243,7 +290,8 @@ def make_workload(outdir, alphabet="dna", n_total=10000, n_backbone=1000, root_l
         names.append("Q%06d" % n)
         seqs.append("".join(lut[r]))
     meta = dict(alphabet=alphabet, n_queries=len(seqs), H=len(hmm_paths), sumL=int(sum(len(s) for s in seqs)),
-                sumM=int(sum(len(c) for c in retained)), backbone_length=int(backbone_length), seed=seed, dir=wd)
+                sumM=int(sum(len(c) for c in retained)), backbone_length=int(backbone_length), seed=seed, dir=wd,
+                profiles=profiles)
     return dict(hmm_paths=hmm_paths, nseq=nseqs, names=names, seqs=seqs, retained_columns=retained,
                 nongaps_per_column=nongaps, backbone_length=backbone_length, meta=meta)
 
