@@ -39,6 +39,8 @@ struct alignas(8) float2 { float x, y; };
 struct uint3 { unsigned x, y, z; };
 struct dim3 { unsigned x = 1, y = 1, z = 1; dim3() {} dim3(unsigned a) : x(a) {} };
 static inline float4 make_float4(float x, float y, float z, float w) { float4 v; v.x = x; v.y = y; v.z = z; v.w = w; return v; }
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 v; v.x = x; v.y = y; v.z = z; v.w = w; return v; }
 static inline float2 make_float2(float x, float y) { float2 v; v.x = x; v.y = y; return v; }
 template <class A, class B> static inline auto min(A a, B b) -> decltype(a + b) { return a < b ? a : b; }
 template <class A, class B> static inline auto max(A a, B b) -> decltype(a + b) { return a > b ? a : b; }
@@ -147,6 +149,8 @@ static inline int __ffs(int x) { return __builtin_ffs(x); }
 template <class T> static inline T __ldg(const T *p) { return *p; }
 static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
 static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
+static inline unsigned __float_as_uint(float f) { unsigned i; std::memcpy(&i, &f, 4); return i; }
+static inline float __uint_as_float(unsigned i) { float f; std::memcpy(&f, &i, 4); return f; }
 template <class T, class U> static inline T atomicAdd(T *p, U v) { T o = *p; *p = o + (T)v; return o; }
 template <class T, class U> static inline T atomicMax(T *p, U v) { T o = *p; if ((T)v > o) *p = (T)v; return o; }
 
@@ -155,6 +159,7 @@ namespace witch {
 static inline unsigned smem_u32(const void *p) { return (unsigned)(int32_t)((const char *)p - simt::g_smem_arena); }
 static inline float4 lds_f4(unsigned a) { return *reinterpret_cast<const float4 *>(simt::sptr(a)); }
 static inline float4 lds_f4v(unsigned a) { return lds_f4(a); }
+static inline uint4 lds_u4v(unsigned a) { return *reinterpret_cast<const uint4 *>(simt::sptr(a)); }
 static inline float lds_f1(unsigned a) { return *reinterpret_cast<const float *>(simt::sptr(a)); }
 static inline float lds_f1v(unsigned a) { return lds_f1(a); }
 static inline void sts_f1(unsigned a, float v) { *reinterpret_cast<float *>(simt::sptr(a)) = v; }

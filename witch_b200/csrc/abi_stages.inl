@@ -89,7 +89,7 @@ static void run_wave_c(witch_ehmm *e, witch_queries *q, std::vector<WaveBucket> 
         const int emis_floats = q->nsym * max_strips * SW;
         const int res_cap = (Lcap + 1 + 15) / 16 * 16;
         const size_t smem = (size_t)emis_floats * sizeof(float) + (size_t)WAVE_WARPS * res_cap +
-                            (size_t)WAVE_WARPS * RING * (wave_ring_stage_bytes(C, ALIGN) + 8) +
+                            (size_t)WAVE_WARPS * RING * (wave_ring_stage_bytes(C, ALIGN, W_ROW16 != 0 && !ALIGN && !LANE_EXP) + 8) +
                             (size_t)WAVE_WARPS * wave_bnd_ring_bytes();
         if (smem > 220 * 1024) throw std::runtime_error("emission table + residue staging do not fit shared memory");
         auto kern = wave_kernel<C, ALIGN, WAVE_WARPS, MINB, RING, LANE_EXP>;

@@ -68,14 +68,41 @@ constexpr int W_UNROLL_F = WITCH_WAVE_UNROLL_F, W_UNROLL_B = WITCH_WAVE_UNROLL_B
 #define WITCH_WAVE_EXP 0
 #endif
 constexpr int W_EXP = WITCH_WAVE_EXP;
+// Stored Forward match rows of the ENVELOPE pass (DNA/RNA, warp-uniform exponent) in 16 bits: halves the pass's HBM traffic
+// (8 -> 4 B/cell). 0 = FP32 rows; 1 = bf16 (round to nearest, 2^-9 relative); 2 = unsigned E8M8 (the values are >= 0, so
+// the sign bit's place is given to the mantissa: bits [30:15] of the FP32, round to nearest, 2^-10 relative).
+#ifndef WITCH_WAVE_ROW16
+#define WITCH_WAVE_ROW16 0
+#endif
+constexpr int W_ROW16 = WITCH_WAVE_ROW16;
+__device__ __forceinline__ unsigned pack_row16(float lo, float hi) {
+    if (W_ROW16 == 1) {
+#ifndef WITCH_HOST_SIM
+        unsigned r;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+        return r;
+#else
+        const unsigned a = __float_as_uint(lo), b = __float_as_uint(hi);   // round to nearest even
+        return ((a + 0x7fffu + ((a >> 16) & 1u)) >> 16) | ((b + 0x7fffu + ((b >> 16) & 1u)) & 0xffff0000u);
+#endif
+    }
+    return (((__float_as_uint(lo) + 0x4000u) >> 15) & 0xffffu) | (((__float_as_uint(hi) + 0x4000u) << 1) & 0xffff0000u);
+}
+__device__ __forceinline__ float unpack_row16_lo(unsigned w) { return __uint_as_float(W_ROW16 == 1 ? (w << 16) : ((w << 15) & 0x7fff8000u)); }
+__device__ __forceinline__ float unpack_row16_hi(unsigned w) { return __uint_as_float(W_ROW16 == 1 ? (w & 0xffff0000u) : ((w >> 1) & 0x7fff8000u)); }
 #ifndef WITCH_HOST_SIM
 __device__ __forceinline__ bool wave_elect_one() {
     unsigned p;
     asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(p));
     return p != 0;
 }
+__device__ __forceinline__ uint4 lds_u4v(unsigned a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
 #endif
-__host__ __device__ constexpr int wave_ring_stage_bytes(int C, bool align) { return 32 * C * 4 * (align ? 2 : 1); }
+__host__ __device__ constexpr int wave_ring_stage_bytes(int C, bool align, bool row16 = false) { return 32 * C * (row16 ? 2 : 4) * (align ? 2 : 1); }
 #ifndef WITCH_HOST_SIM
 // ---- TMA (1-D bulk async copy) + mbarrier: completion is tracked in shared memory, not on a register scoreboard
 __device__ __forceinline__ void mbar_init(unsigned bar, int count) {
@@ -119,7 +146,8 @@ struct WaveLayout {
 __host__ __device__ inline WaveLayout wave_layout(int Lcap, int max_strips, int C, bool align, bool lane_exp) {
     WaveLayout w;
     w.TT = Lcap + 32;
-    long long tile = (long long)max_strips * w.TT * 32 * C * 4;
+    const bool row16 = W_ROW16 != 0 && !align && !lane_exp;
+    long long tile = (long long)max_strips * w.TT * 32 * C * (row16 ? 2 : 4);
     long long o = 0;
     w.tileM = o; o += tile;
     w.tileI = o; if (align) o += tile;  // insert rows are kept for the align stage only
@@ -188,6 +216,9 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, 
 #define GF_AT(blk) (LANE_EXP ? (blk) * 32 + lane : (blk))
     const unsigned emis_sa = smem_u32(emis_s);
     const int SW = 32 * C;  // strip width
+    constexpr bool ROW16 = W_ROW16 != 0 && !ALIGN && !LANE_EXP;   // stored Forward match rows in 16 bits (envelope pass, DNA/RNA)
+    static_assert(!ROW16 || C == 8, "16-bit rows: one 128-bit word per lane and step");
+    constexpr int TSTEP = ROW16 ? 32 * C / 2 : 32 * C;   // floats (4-byte words) of one stored step of a strip
 
     // ring state persists across strips and items (the mbarriers are initialised once; phases keep alternating)
     int rd_stage = 0, wr_stage = 0;
@@ -195,7 +226,7 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, 
     int bq_w = 0, bq_r = 0;   // boundary-record ring: next slot to fill / to wait for
     unsigned bq_ph = 0;
     // dynamic shared memory after the emission table: residues | Forward-row ring | its mbarriers | boundary ring | its mbarriers
-    constexpr int RSB = wave_ring_stage_bytes(C, ALIGN);
+    constexpr int RSB = wave_ring_stage_bytes(C, ALIGN, ROW16);
     const unsigned sm_dyn = emis_sa + Wk.emis_floats * 4;
     const unsigned ring_w = sm_dyn + WAVE_WARPS * Wk.res_cap + w * (W_RING * RSB);
     const unsigned ring_sa = ring_w + lane * 16;
@@ -289,10 +320,10 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, 
             const bool last = (s == nstrips - 1);
             unsigned ebase = emis_sa + (s * SW + lane * 4) * 4;
             unsigned erow = Mstr * 4;
-            float *tM = tileM + (size_t)s * TT * SW, *tI = tileI + (size_t)s * TT * SW;
+            float *tM = tileM + (size_t)s * TT * TSTEP, *tI = tileI + (size_t)s * TT * SW;
             // wave-layout tile of a strip: [step t][v][lane][4 floats] -- every 128-bit access of a warp is one
-            // contiguous 512-byte run (v-th quad of the lane's C columns)
-            int toff = 32 * C + lane * 4;  // element offset of (step t, lane) quad 0
+            // contiguous 512-byte run (v-th quad of the lane's C columns); 16-bit rows: [step t][lane][8 x 16 bit]
+            int toff = TSTEP + lane * 4;  // element offset of (step t, lane) quad 0
             int *gFs = gFarr + s * TG;
             unsigned sresp = sres;
             PIN32(ebase); PIN32(erow); PIN64(tM); PIN64(gFs); PIN32(sresp);
@@ -373,10 +404,15 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, 
                     float *dm = tMp, *di = tIp;
                     // (envelope mode needs match posteriors only: sum over emitting states of a row's posteriors is 1,
                     //  so fI + fNCJ = 1 - sum_k fM(k); insert rows are stored for the align stage only)
+                    if (ROW16) {
+                        *reinterpret_cast<uint4 *>(dm) = make_uint4(pack_row16(nM[0], nM[1]), pack_row16(nM[2], nM[3]),
+                                                                    pack_row16(nM[4], nM[5]), pack_row16(nM[C - 2], nM[C - 1]));
+                    } else {
 #pragma unroll
-                    for (int v = 0; v < C / 4; v++) {
-                        *reinterpret_cast<float4 *>(dm + 128 * v) = make_float4(nM[4 * v], nM[4 * v + 1], nM[4 * v + 2], nM[4 * v + 3]);
-                        if (ALIGN) *reinterpret_cast<float4 *>(di + 128 * v) = make_float4(nI[4 * v], nI[4 * v + 1], nI[4 * v + 2], nI[4 * v + 3]);
+                        for (int v = 0; v < C / 4; v++) {
+                            *reinterpret_cast<float4 *>(dm + 128 * v) = make_float4(nM[4 * v], nM[4 * v + 1], nM[4 * v + 2], nM[4 * v + 3]);
+                            if (ALIGN) *reinterpret_cast<float4 *>(di + 128 * v) = make_float4(nI[4 * v], nI[4 * v + 1], nI[4 * v + 2], nI[4 * v + 3]);
+                        }
                     }
                     if (lane == 31) {
                         if (!last) { BND_V(i) = make_float4(sM[C - 1], sI[C - 1], sD[C - 1], ep); BND_G(i) = g; }
@@ -388,7 +424,7 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, 
                         }
                     }
                 }
-                tMp += 32 * C;
+                tMp += TSTEP;
                 if (ALIGN) tIp += 32 * C;
             };
             // every 8 steps: record the exponent of the block (for the Backward pass) / renormalise
@@ -487,7 +523,7 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, 
             const int rs = (lane == 31) ? s + 1 : s, rl = (lane == 31) ? 0 : lane + 1;
             const bool hasR = !(lastS && lane == 31);
             unsigned eright = emis_sa + (rs * SW + emis_index<C>(32, rl, 0)) * 4;
-            float *tM = tileM + (size_t)s * TT * SW, *tI = tileI + (size_t)s * TT * SW;
+            float *tM = tileM + (size_t)s * TT * TSTEP, *tI = tileI + (size_t)s * TT * SW;
             const int *gFs = gFarr + s * TG;
             unsigned sresp = sres;
             PIN32(ebase); PIN32(erow); PIN32(eright); PIN64(tM); PIN64(gFs); PIN32(sresp);
@@ -506,7 +542,7 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, 
             // Stored Forward rows come back through a shared-memory ring filled by TMA bulk copies, W_RING-1 steps ahead
             // of their use (one lane issues one copy per step: the step's rows of all 32 lanes are one contiguous run;
             // completion is an mbarrier transaction count, so no register scoreboard is tied up by the prefetch).
-            const float *tMrd = tM + (size_t)(Ls + 31) * 32 * C;   // rows of step 0; step tq is 32*C floats earlier
+            const float *tMrd = tM + (size_t)(Ls + 31) * TSTEP;   // rows of step 0; step tq is TSTEP words earlier
             const float *tIrd = tI + (size_t)(Ls + 31) * 32 * C;
             float *tMw = tM + (size_t)(Ls + 31) * 32 * C + lane * 4, *tIw = tI + (size_t)(Ls + 31) * 32 * C + lane * 4;
             int tq_next = 0;   // next step whose rows have not been requested yet
@@ -514,10 +550,10 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, 
                 if ((W_EXP & 1) ? wave_elect_one() : (lane == 0)) {
                     const unsigned dst = ring_w + wr_stage * RSB, bar = ring_bar + wr_stage * 8;
                     mbar_expect_tx(bar, RSB);
-                    tma_load_1d(dst, tMrd, 32 * C * 4, bar);
+                    tma_load_1d(dst, tMrd, TSTEP * 4, bar);
                     if (ALIGN) tma_load_1d(dst + 32 * C * 4, tIrd, 32 * C * 4, bar);
                 }
-                tMrd -= 32 * C;
+                tMrd -= TSTEP;
                 if (ALIGN) tIrd -= 32 * C;
                 wr_stage = (wr_stage == W_RING - 1) ? 0 : wr_stage + 1;
                 tq_next++;
@@ -606,10 +642,17 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, 
                         }
                         // posterior decoding against the stored forward row (this step's ring stage is complete)
                         float FMv[C], FIv[C];
+                        if (ROW16) {
+                            const uint4 a = lds_u4v(rs);
+                            FMv[0] = unpack_row16_lo(a.x); FMv[1] = unpack_row16_hi(a.x); FMv[2] = unpack_row16_lo(a.y); FMv[3] = unpack_row16_hi(a.y);
+                            FMv[4] = unpack_row16_lo(a.z); FMv[5] = unpack_row16_hi(a.z); FMv[C - 2] = unpack_row16_lo(a.w); FMv[C - 1] = unpack_row16_hi(a.w);
+                        }
 #pragma unroll
                         for (int v = 0; v < C / 4; v++) {
-                            const float4 a = lds_f4v(rs + v * 512);
-                            FMv[4 * v] = a.x; FMv[4 * v + 1] = a.y; FMv[4 * v + 2] = a.z; FMv[4 * v + 3] = a.w;
+                            if (!ROW16) {
+                                const float4 a = lds_f4v(rs + v * 512);
+                                FMv[4 * v] = a.x; FMv[4 * v + 1] = a.y; FMv[4 * v + 2] = a.z; FMv[4 * v + 3] = a.w;
+                            }
                             if (ALIGN) {
                                 const float4 b = lds_f4v(rs + 32 * C * 4 + v * 512);
                                 FIv[4 * v] = b.x; FIv[4 * v + 1] = b.y; FIv[4 * v + 2] = b.z; FIv[4 * v + 3] = b.w;
