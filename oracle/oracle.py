@@ -41,9 +41,10 @@ AMINO_BG = [0.0787945, 0.0151600, 0.0535222, 0.0668298, 0.0397062, 0.0695071, 0.
 def build_lib(force=False):
     """Compile hmm_oracle.c -> oracle/liboracle.so (gcc)."""
     so = os.path.join(_HERE, "liboracle.so")
-    src = os.path.join(_HERE, "hmm_oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
-        subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-o", so, src, "-lm"])
+    srcs = [os.path.join(_HERE, "hmm_oracle.c"), os.path.join(_HERE, "hmm_md.c")]
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(x) for x in srcs):
+        # -ffp-contract=off: hmm_md.c restates HMMER's SSE float arithmetic operation by operation (no FMA contraction)
+        subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", so] + srcs + ["-lm"])
     return so
 
 
@@ -54,6 +55,8 @@ def lib():
         _LIB.orc_forward.restype = ctypes.c_double
         _LIB.orc_backward.restype = ctypes.c_double
         _LIB.orc_graph_dp.restype = ctypes.c_int
+        _LIB.md_oprofile_create.restype = ctypes.c_void_p
+        _LIB.md_oprofile_free.argtypes = [ctypes.c_void_p]
     return _LIB
 
 
@@ -132,20 +135,31 @@ class Profile:
         def p(v):
             return 0.0 if v == "*" else math.exp(-float(v))
 
+        def raw(v):
+            return math.inf if v == "*" else float(v)
+
         ln = next(it).split()
         if ln[0] == "COMPO":
             ln = next(it).split()
         # ln = node-0 insert emissions (ignored); next: node-0 transitions
-        t0 = [p(v) for v in next(it).split()]
+        tok0 = next(it).split()
+        t0 = [p(v) for v in tok0]
         self.mat = np.zeros((M + 1, K))
         self.t = np.zeros((M + 1, 7))
         self.t[0] = t0
+        # the numbers of the text file as written (-ln p, inf for '*'): input of the float restatement in hmm_md.c
+        self.raw_t = np.full((M + 1, 7), np.inf)
+        self.raw_mat = np.full((M + 1, K), np.inf)
+        self.raw_t[0] = [raw(v) for v in tok0]
         for k in range(1, M + 1):
             tok = next(it).split()
             assert int(tok[0]) == k, (tok, k)
             self.mat[k] = [p(v) for v in tok[1:1 + K]]
+            self.raw_mat[k] = [raw(v) for v in tok[1:1 + K]]
             next(it)  # insert emissions: ignored (insert score hard-wired to 0)
-            self.t[k] = [p(v) for v in next(it).split()]
+            tokt = next(it).split()
+            self.t[k] = [p(v) for v in tokt]
+            self.raw_t[k] = [raw(v) for v in tokt]
 
     def _config(self):
         M, K, Kp = self.M, self.abc.K, self.abc.Kp
@@ -195,16 +209,40 @@ def backward_nats(prof, dsq, multihit=True, Lmodel=None):
     return lib().orc_backward(prof.M, prof.abc.Kp, *prof._args(), _u8(dsq), L, int(multihit), Lmodel or L)
 
 
-def score_pair(prof, dsq):
-    """dict(reported, pre_score, score, nregions, flags, env, ...) for one (profile, digitized sequence)."""
-    res = np.zeros(12)
+def oprofile(prof):
+    """Handle of the float restatement of HMMER's optimized profile (hmm_md.c), cached on the Profile."""
+    if getattr(prof, "_om", None) is None:
+        ip = ctypes.POINTER(ctypes.c_int)
+        dp = ctypes.POINTER(ctypes.c_double)
+        prof._bg32 = np.ascontiguousarray(prof.abc.bg, dtype=np.float32)
+        prof._raw_t = np.ascontiguousarray(prof.raw_t, dtype=np.float64)
+        prof._raw_mat = np.ascontiguousarray(prof.raw_mat, dtype=np.float64)
+        prof._om = ctypes.c_void_p(lib().md_oprofile_create(
+            prof.M, prof.abc.K, prof.abc.Kp, prof._raw_t.ctypes.data_as(dp), prof._raw_mat.ctypes.data_as(dp),
+            prof._bg32.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+            prof.abc.degen_n.ctypes.data_as(ip), prof.abc.degen_set.ctypes.data_as(ip)))
+    return prof._om
+
+
+def score_pair(prof, dsq, multidomain=True):
+    """dict(reported, pre_score, score, nregions, flags, env, envelopes, ...) for one (profile, digitized sequence).
+    multidomain=True: regions that fail the single-domain test go through HMMER's stochastic-trace clustering
+    (hmm_md.c); False: such a region is kept as one envelope (the round-1 simplification, for comparison)."""
+    res = np.zeros(13)
+    env = np.zeros((64, 5))
+    sig = np.zeros((128, 5), dtype=np.int32)
+    nsig = ctypes.c_int(0)
     ip = ctypes.POINTER(ctypes.c_int)
-    lib().orc_score_pair(prof.M, prof.abc.Kp, prof.abc.K, *prof._args(),
-                         prof.abc.degen_n.ctypes.data_as(ip), prof.abc.degen_set.ctypes.data_as(ip),
-                         _u8(dsq), len(dsq), res.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib().orc_score_pair2(prof.M, prof.abc.Kp, prof.abc.K, *prof._args(),
+                          prof.abc.degen_n.ctypes.data_as(ip), prof.abc.degen_set.ctypes.data_as(ip),
+                          _u8(dsq), len(dsq), oprofile(prof) if multidomain else None,
+                          res.ctypes.data_as(dp), env.ctypes.data_as(dp), 64, sig.ctypes.data_as(ip), 128, ctypes.byref(nsig))
+    nenv = int(res[12])
     return dict(reported=bool(res[0]), pre_score=res[1], score=res[2], nregions=int(res[3]), flags=int(res[4]),
                 env=(int(res[5]), int(res[6])), fwd=res[7], max_mocc=res[8], mdstat=res[9], seq_score=res[10],
-                sum_score=res[11])
+                sum_score=res[11], nenv=nenv, clusters=[tuple(int(x) for x in c) for c in sig[:min(nsig.value, 128)]],
+                envelopes=[(int(e[0]), int(e[1]), float(e[2]), float(e[3]), bool(e[4])) for e in env[:min(nenv, 64)]])
 
 
 def align_pair(prof, dsq):
