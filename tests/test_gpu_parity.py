@@ -54,21 +54,23 @@ def test_scores_weights_columns_vs_oracle_and_golden(wb, setname, tmp_path):
             assert abs(sc[qi, h] - r["score"]) < tol, (setname, qi, h, sc[qi, h], r)
         else:
             assert np.isnan(sc[qi, h])
-    # printed 1-decimal scores against the reference binary (non multi-domain pairs; values within 1e-3 of a
-    # rounding boundary may legitimately print differently)
+    # printed 1-decimal scores against the reference binary, multi-domain pairs included (values within 1e-3 of a
+    # rounding boundary may legitimately print differently); the reported sets must be hmmsearch's
     names = [n for n, _ in queries]
-    nprint = 0
+    nprint = nmd = 0
     for h, hg in enumerate(gold["hmms"]):
+        assert {names[qi] for qi in range(Q.n) if rep[qi, h]} == set(hg["hits"].keys()), (setname, h)
         for n, hit in hg["hits"].items():
             qi = names.index(n)
-            if fl[qi, h] & 1 or not rep[qi, h]:
-                continue
+            nmd += int(fl[qi, h] & 1)
             x = float(sc[qi, h]) * 10.0
             if abs(x - np.floor(x) - 0.5) < 0.01:
                 continue
             assert O.printed_score(float(sc[qi, h])) == hit["score"], (setname, n, h, sc[qi, h], hit)
             nprint += 1
     assert nprint > 0
+    if setname in ("dna_small", "dna_sub8", "dna_full", "amino_extreme"):
+        assert nmd >= 10   # these sets exercise the multi-domain branch (stochastic-trace clustering) on the device
     # weights / top-k
     idx, w, cnt = wb.weights_topk(E, sc, rep, 10, 1)
     for qi in range(Q.n):
@@ -180,8 +182,8 @@ def test_mirror_interface_end_to_end(wb, tmp_path):
     for h, hg in enumerate(gold["hmms"]):
         res = bs.hmmsearch_results(h)
         for n, hit in hg["hits"].items():
-            if n in res and not (bs.flags[names.index(n), h] & 1):
-                assert abs(res[n][1] - hit["score"]) <= 0.1 + 1e-9
+            assert n in res
+            assert abs(res[n][1] - hit["score"]) <= 0.1 + 1e-9
     for t, sw in t2w.items():
         assert isinstance(sw, tuple) and all(isinstance(i, int) and isinstance(x, float) for i, x in sw)
         assert [x[1] for x in ranked[t]] == sorted((x[1] for x in ranked[t]), reverse=True)
@@ -263,7 +265,7 @@ def test_graph_dp_full_device_path_vs_oracle(wb, tmp_path):
         assert rows[taxon].replace("-", "").upper() == seq.upper()
         if taxon in G["queries"] and rows[taxon] == G["queries"][taxon]["row"]:
             nsame_ref += 1
-    assert nsame_ref >= len(G["queries"]) - 3   # documented: multi-domain-flagged extras / one near-tie alignment
+    assert nsame_ref >= len(G["queries"]) - 1   # documented: one FP32 near-tie alignment (2 of 35,293 residues)
 
 
 def test_merge_matches_reference_python(wb, tmp_path):

@@ -43,15 +43,19 @@ t0 = time.time()
 sc, rep, pre, fl = wb.score(E, Q)
 print("score stage simulated in %.1f s" % (time.time() - t0))
 worst = wpre = wbias = 0.0
+nmd = 0
 for qi in range(Q.n):
     for h in range(E.n):
         r = O.score_pair(profs[h], profs[h].abc.digitize(queries[qi][1]))
         assert bool(rep[qi, h]) == r["reported"], (qi, h, r, sc[qi, h])
+        assert (int(fl[qi, h]) & 1) == (r["flags"] & 1), (qi, h, fl[qi, h], r)
+        nmd += r["flags"] & 1
         wpre = max(wpre, abs(float(pre[qi, h]) - r["pre_score"]))
         if r["reported"]:
             worst = max(worst, abs(float(sc[qi, h]) - r["score"]))
             wbias = max(wbias, r["pre_score"] - r["score"])
-print("parser + envelope kernels: reported sets identical, max |dpre| %.2e bits, max |dscore| %.2e bits (largest null2 correction %.2f bits)" % (wpre, worst, wbias))
+print("parser + multi-domain + envelope kernels: reported sets identical, %d of %d pairs through the multi-domain branch, max |dpre| %.2e bits, "
+      "max |dscore| %.2e bits (largest null2 correction %.2f bits)" % (nmd, Q.n * E.n, wpre, worst, wbias))
 assert wpre < 1e-3 and worst < 1e-3
 idx, w, cnt = wb.weights_topk(E, sc, rep, 10, 1)
 pq = [qi for qi in range(Q.n) if cnt[qi] > 0][:nalign]

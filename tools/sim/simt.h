@@ -153,6 +153,7 @@ static inline unsigned __float_as_uint(float f) { unsigned i; std::memcpy(&i, &f
 static inline float __uint_as_float(unsigned i) { float f; std::memcpy(&f, &i, 4); return f; }
 template <class T, class U> static inline T atomicAdd(T *p, U v) { T o = *p; *p = o + (T)v; return o; }
 template <class T, class U> static inline T atomicMax(T *p, U v) { T o = *p; if ((T)v > o) *p = (T)v; return o; }
+template <class T, class U> static inline T atomicOr(T *p, U v) { T o = *p; *p = o | (T)v; return o; }
 
 // ---------------------------------------------------------------- host versions of the PTX helpers of the kernels
 namespace witch {
@@ -189,6 +190,8 @@ template <class T> static inline cudaError_t cudaMalloc(T **p, size_t n) {
     return *p ? 0 : 2;
 }
 static inline cudaError_t cudaFree(void *p) { free(p); return 0; }
+template <class T> static inline cudaError_t cudaMallocHost(T **p, size_t n) { *p = (T *)calloc(1, n); return *p ? 0 : 2; }
+static inline cudaError_t cudaFreeHost(void *p) { free(p); return 0; }
 static inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { std::memcpy(d, s, n); return 0; }
 static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { std::memcpy(d, s, n); return 0; }
 static inline cudaError_t cudaMemcpy2D(void *d, size_t dp, const void *s, size_t sp, size_t w, size_t h, cudaMemcpyKind) {

@@ -12,47 +12,19 @@ struct HostClock {   // WITCH_TIMING=1: wall-clock of the host-side phases of a 
     }
 };
 
-struct WaveBucket { int Lcap; std::vector<WaveItem> items; };
+// ---------------------------------------------------------------------------------------------------------------
+// Wavefront launches. One launch = one bucket (length class x model-size class) of a SORTED device item list; the group
+// list and the {first, end} group pair of the bucket live on the device (built by worklist_kernels.cuh for the score
+// stage, uploaded from the host for the align stage), so a sequence of launches needs no synchronisation in between.
+struct WaveLaunch {
+    int item_end = 0;        // items of the bucket end here
+    int Lcap = 0, maxM = 0;  // longest envelope / model of the bucket
+    long long nitems = 0;
+    double cells = 0;
+    const int *grange = nullptr;  // device {first group, end group}
+    unsigned *counter = nullptr;  // device work counter of this launch (zeroed by the caller)
+};
 
-// Length classes of the wavefront launches (scratch and residue staging are sized by the longest item of a launch).
-static const int WAVE_CAPS[] = {256, 512, 1024, 2048, 4096, 1 << 30};
-static inline int wave_bucket_of(int Ls) { int b = 0; while (Ls > WAVE_CAPS[b]) b++; return b; }
-
-// rank of every HMM in launch order: longer models first (stable)
-static std::vector<int> model_rank(const witch_ehmm *e) {
-    std::vector<int> hrank(e->H), horder(e->H);
-    std::iota(horder.begin(), horder.end(), 0);
-    std::stable_sort(horder.begin(), horder.end(), [&](int a, int b) { return e->M[a] > e->M[b]; });
-    for (int r = 0; r < e->H; r++) hrank[horder[r]] = r;
-    return hrank;
-}
-
-// Generic path (align stage, debug hooks): bucket by length, then order each bucket by (model rank, longer envelopes
-// first) with two stable counting passes (LSD radix; no comparison sort over millions of items).
-static std::vector<WaveBucket> bucketize_items(const witch_ehmm *e, const std::vector<WaveItem> &items) {
-    // 6 length classes x 2 model-size classes: models beyond 13 strips (3,328 nodes) get their own launches so that
-    // their shared-memory emission table does not set the occupancy of everything else
-    std::vector<WaveBucket> buckets(12);
-    for (auto &it : items) buckets[2 * wave_bucket_of(it.Ls) + (e->M[it.h] > 13 * 256 ? 1 : 0)].items.push_back(it);
-    const std::vector<int> hrank = model_rank(e);
-    for (auto &bk : buckets) {
-        if (bk.items.empty()) continue;
-        int Lcap = 0;
-        for (auto &it : bk.items) Lcap = std::max(Lcap, it.Ls);
-        std::vector<WaveItem> tmp(bk.items.size());
-        std::vector<size_t> cnt((size_t)Lcap + 2, 0);
-        for (auto &it : bk.items) cnt[Lcap - it.Ls + 1]++;                 // key 2: Ls descending
-        for (size_t k = 1; k < cnt.size(); k++) cnt[k] += cnt[k - 1];
-        for (auto &it : bk.items) tmp[cnt[Lcap - it.Ls]++] = it;
-        cnt.assign((size_t)e->H + 1, 0);
-        for (auto &it : tmp) cnt[hrank[it.h] + 1]++;                       // key 1: model rank
-        for (size_t k = 1; k < cnt.size(); k++) cnt[k] += cnt[k - 1];
-        for (auto &it : tmp) bk.items[cnt[hrank[it.h]]++] = it;
-    }
-    return buckets;
-}
-
-// Launches the wavefront kernel over pre-ordered buckets (items of one HMM contiguous); outputs indexed by WaveItem::pair.
 // envelope-mode launch shape: warps per CTA x resident CTAs per SM. 4 x 3 (12 warps/SM, 168 registers) is the measured
 // optimum: 6 x 2 -3 %, 2 x 6 -35 % (six emission tables per SM), 8 x 2 (128 registers, spills) -38 % -- DESIGN.md section 8
 #ifndef WITCH_ENV_WARPS
@@ -62,150 +34,197 @@ static std::vector<WaveBucket> bucketize_items(const witch_ehmm *e, const std::v
 #define WITCH_ENV_MINB 3
 #endif
 template <bool ALIGN, int C, int WAVE_WARPS, int MINB, int RING, bool LANE_EXP>
-static void run_wave_c(witch_ehmm *e, witch_queries *q, std::vector<WaveBucket> &buckets, float *d_envsc, float *d_domcorr,
-                     int *d_cols, const long long *d_coloff, float *d_dbg_fwd, float *d_dbg_bwd, cudaStream_t st) {
+static void run_wave_c(witch_ehmm *e, witch_queries *q, const WaveItem *d_items, const int *d_group_first,
+                       const std::vector<WaveLaunch> &launches, float *d_envsc, float *d_domcorr, int *d_cols,
+                       const long long *d_coloff, float *d_dbg_fwd, float *d_dbg_bwd, cudaStream_t st) {
     const int SW = 32 * C;
+    constexpr bool ROW16 = W_ROW16 != 0 && !ALIGN && !LANE_EXP;
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
     const double budget = std::min<double>(64.0e9, 0.5 * (double)(free_b + e->bytes.n));
-    for (auto &bk : buckets) {
-        if (bk.items.empty()) continue;
-        int Lcap = 0, max_strips = 1, maxM = 0;
-        double cells = 0;
-        for (auto &it : bk.items) {
-            Lcap = std::max(Lcap, it.Ls);
-            maxM = std::max(maxM, e->M[it.h]);
-            cells += (double)it.Ls * e->M[it.h];
-        }
-        max_strips = (maxM + SW - 1) / SW;
-        std::vector<int> gfirst, gcount;
-        for (size_t i = 0; i < bk.items.size();) {
-            size_t j = i;
-            while (j < bk.items.size() && bk.items[j].h == bk.items[i].h && j - i < (size_t)WAVE_WARPS) j++;
-            gfirst.push_back((int)i); gcount.push_back((int)(j - i));
-            i = j;
-        }
-        const WaveLayout lay = wave_layout(Lcap, max_strips, C, ALIGN, LANE_EXP);
-        const int emis_floats = q->nsym * max_strips * SW;
-        const int res_cap = (Lcap + 1 + 15) / 16 * 16;
-        const size_t smem = (size_t)emis_floats * sizeof(float) + (size_t)WAVE_WARPS * res_cap +
-                            (size_t)WAVE_WARPS * RING * (wave_ring_stage_bytes(C, ALIGN, W_ROW16 != 0 && !ALIGN && !LANE_EXP) + 8) +
-                            (size_t)WAVE_WARPS * wave_bnd_ring_bytes();
-        if (smem > 220 * 1024) throw std::runtime_error("emission table + residue staging do not fit shared memory");
-        auto kern = wave_kernel<C, ALIGN, WAVE_WARPS, MINB, RING, LANE_EXP>;
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = wave_kernel<C, ALIGN, WAVE_WARPS, MINB, RING, LANE_EXP>;
+    struct Plan { WaveLayout lay; int max_strips, emis_floats, res_cap; size_t smem; long long grid; };
+    std::vector<Plan> plans;
+    size_t need = 0;
+    for (auto &L : launches) {   // plan every launch first: the scratch must not be reallocated while launches are in flight
+        Plan P;
+        P.max_strips = (L.maxM + SW - 1) / SW;
+        P.lay = wave_layout(L.Lcap, P.max_strips, C, ALIGN, LANE_EXP);
+        P.emis_floats = q->nsym * P.max_strips * SW;
+        P.res_cap = (L.Lcap + 1 + 15) / 16 * 16;
+        P.smem = (size_t)P.emis_floats * sizeof(float) + (size_t)WAVE_WARPS * P.res_cap +
+                 (size_t)WAVE_WARPS * RING * (wave_ring_stage_bytes(C, ALIGN, ROW16) + 8) + (size_t)WAVE_WARPS * wave_bnd_ring_bytes();
+        if (P.smem > 220 * 1024) throw std::runtime_error("emission table + residue staging do not fit shared memory");
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
         int occ = 1;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WAVE_WARPS * 32, smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WAVE_WARPS * 32, P.smem));
         if (occ < 1) throw std::runtime_error("wave kernel cannot be resident");
-        long long grid = std::min<long long>((long long)gfirst.size(), (long long)e->num_sms * occ);
-        const long long max_slots = (long long)(budget / (double)lay.total);
+        // (every item may be its own group in the worst case; the kernel reads the true group range from the device)
+        long long grid = std::min<long long>(L.nitems, (long long)e->num_sms * occ);
+        const long long max_slots = (long long)(budget / (double)P.lay.total);
         if (max_slots < WAVE_WARPS) throw std::runtime_error("not enough device memory for the wave scratch");
-        grid = std::max<long long>(1, std::min<long long>(grid, max_slots / WAVE_WARPS));
-        e->bytes.alloc((size_t)grid * WAVE_WARPS * lay.total);
-        DevBuf<WaveItem> ditems; ditems.upload(bk.items, st);
-        DevBuf<int> dgf, dgc; dgf.upload(gfirst, st); dgc.upload(gcount, st);
-        e->counter.alloc(64);
-        CUDA_TRY(cudaMemsetAsync(e->counter.p, 0, sizeof(unsigned), st));
+        P.grid = std::max<long long>(1, std::min<long long>(grid, max_slots / WAVE_WARPS));
+        need = std::max<size_t>(need, (size_t)((long long)P.grid * WAVE_WARPS * P.lay.total));
+        plans.push_back(P);
+    }
+    if (need > e->bytes.n) { CUDA_TRY(cudaStreamSynchronize(st)); e->bytes.alloc(need); }   // grows during warm-up only
+    for (size_t z = 0; z < launches.size(); z++) {
+        const WaveLaunch &L = launches[z];
+        const Plan &P = plans[z];
         WaveWork wk;
-        wk.items = ditems.p; wk.group_first = dgf.p; wk.group_count = dgc.p; wk.ngroups = (int)gfirst.size();
-        wk.counter = e->counter.p; wk.scratch = (char *)e->bytes.p; wk.slot_bytes = lay.total; wk.Lcap = Lcap;
-        wk.max_strips = max_strips; wk.emis_floats = emis_floats; wk.res_cap = res_cap; wk.envsc = d_envsc; wk.domcorr = d_domcorr; wk.cols = d_cols; wk.col_off = d_coloff;
-        wk.dbg_fwd = d_dbg_fwd; wk.dbg_bwd = d_dbg_bwd;
-        {
-            ScopedTimer tm(ALIGN ? 2 : 1, st, cells);
-            WITCH_LAUNCH(kern, (int)grid, WAVE_WARPS * 32, smem, st)(e->view(), q->view(), wk);
-            g_launches++;
-            CUDA_TRY(cudaGetLastError());
-        }
-        CUDA_TRY(cudaStreamSynchronize(st));  // ditems/dgf/dgc are freed at scope exit
+        wk.items = d_items; wk.group_first = d_group_first; wk.grange = L.grange; wk.item_end = L.item_end;
+        wk.counter = L.counter; wk.scratch = (char *)e->bytes.p; wk.slot_bytes = P.lay.total; wk.Lcap = L.Lcap;
+        wk.max_strips = P.max_strips; wk.emis_floats = P.emis_floats; wk.res_cap = P.res_cap; wk.envsc = d_envsc; wk.domcorr = d_domcorr;
+        wk.cols = d_cols; wk.col_off = d_coloff; wk.dbg_fwd = d_dbg_fwd; wk.dbg_bwd = d_dbg_bwd;
+        ScopedTimer tm(ALIGN ? 2 : 1, st, L.cells);
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
+        WITCH_LAUNCH(kern, (int)P.grid, WAVE_WARPS * 32, P.smem, st)(e->view(), q->view(), wk);
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
     }
 }
-
-#if WITCH_WAVE_PAIR
-// Envelope pass with two items per warp (wave_pair_kernel.cuh; build-time option, DNA/RNA alphabets only).
-template <int WAVE_WARPS, int MINB, int RING>
-static void run_wave_pair(witch_ehmm *e, witch_queries *q, std::vector<WaveBucket> &buckets, float *d_envsc, float *d_domcorr,
-                          cudaStream_t st) {
-    size_t free_b = 0, total_b = 0;
-    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-    const double budget = std::min<double>(64.0e9, 0.5 * (double)(free_b + e->bytes.n));
-    for (auto &bk : buckets) {
-        if (bk.items.empty()) continue;
-        int Lcap = 0, maxM = 0;
-        double cells = 0;
-        for (auto &it : bk.items) {
-            Lcap = std::max(Lcap, it.Ls);
-            maxM = std::max(maxM, e->M[it.h]);
-            cells += (double)it.Ls * e->M[it.h];
-        }
-        const int max_strips = (maxM + WP_SW - 1) / WP_SW;
-        std::vector<int> gfirst, gcount;
-        for (size_t i = 0; i < bk.items.size();) {   // groups of up to 2 x WAVE_WARPS consecutive items of one HMM
-            size_t j = i;
-            while (j < bk.items.size() && bk.items[j].h == bk.items[i].h && j - i < (size_t)(2 * WAVE_WARPS)) j++;
-            gfirst.push_back((int)i); gcount.push_back((int)(j - i));
-            i = j;
-        }
-        const WavePairLayout lay = wave_pair_layout(Lcap, max_strips);
-        const int emis_floats = q->nsym * max_strips * WP_SW;
-        const int res_cap = (Lcap + 1 + 15) / 16 * 16;
-        const size_t smem = (size_t)emis_floats * sizeof(float) + (size_t)WAVE_WARPS * wave_pair_smem_per_warp(RING, res_cap);
-        if (smem > 220 * 1024) throw std::runtime_error("emission table + residue staging do not fit shared memory");
-        auto kern = wave_pair_kernel<WAVE_WARPS, MINB, RING>;
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int occ = 1;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WAVE_WARPS * 32, smem));
-        if (occ < 1) throw std::runtime_error("wave pair kernel cannot be resident");
-        long long grid = std::min<long long>((long long)gfirst.size(), (long long)e->num_sms * occ);
-        const long long max_slots = (long long)(budget / (double)lay.total);
-        if (max_slots < WAVE_WARPS) throw std::runtime_error("not enough device memory for the wave scratch");
-        grid = std::max<long long>(1, std::min<long long>(grid, max_slots / WAVE_WARPS));
-        e->bytes.alloc((size_t)grid * WAVE_WARPS * lay.total);
-        DevBuf<WaveItem> ditems; ditems.upload(bk.items, st);
-        DevBuf<int> dgf, dgc; dgf.upload(gfirst, st); dgc.upload(gcount, st);
-        e->counter.alloc(64);
-        CUDA_TRY(cudaMemsetAsync(e->counter.p, 0, sizeof(unsigned), st));
-        WaveWork wk;
-        wk.items = ditems.p; wk.group_first = dgf.p; wk.group_count = dgc.p; wk.ngroups = (int)gfirst.size();
-        wk.counter = e->counter.p; wk.scratch = (char *)e->bytes.p; wk.slot_bytes = lay.total; wk.Lcap = Lcap;
-        wk.max_strips = max_strips; wk.emis_floats = emis_floats; wk.res_cap = res_cap; wk.envsc = d_envsc; wk.domcorr = d_domcorr;
-        wk.cols = nullptr; wk.col_off = nullptr; wk.dbg_fwd = nullptr; wk.dbg_bwd = nullptr;
-        {
-            ScopedTimer tm(1, st, cells);
-            WITCH_LAUNCH(kern, (int)grid, WAVE_WARPS * 32, smem, st)(e->view(), q->view(), wk);
-            g_launches++;
-            CUDA_TRY(cudaGetLastError());
-        }
-        CUDA_TRY(cudaStreamSynchronize(st));
-    }
-}
-#endif
 
 template <bool ALIGN>
-static void run_wave(witch_ehmm *e, witch_queries *q, std::vector<WaveBucket> &buckets, float *d_envsc, float *d_domcorr,
-                     int *d_cols, const long long *d_coloff, float *d_dbg_fwd, float *d_dbg_bwd, cudaStream_t st) {
-#define WV_ARGS e, q, buckets, d_envsc, d_domcorr, d_cols, d_coloff, d_dbg_fwd, d_dbg_bwd, st
+static void run_wave(witch_ehmm *e, witch_queries *q, const WaveItem *d_items, const int *d_group_first,
+                     const std::vector<WaveLaunch> &launches, float *d_envsc, float *d_domcorr, int *d_cols,
+                     const long long *d_coloff, float *d_dbg_fwd, float *d_dbg_bwd, cudaStream_t st) {
+    if (launches.empty()) return;
+#define WV_ARGS e, q, d_items, d_group_first, launches, d_envsc, d_domcorr, d_cols, d_coloff, d_dbg_fwd, d_dbg_bwd, st
     const bool lane_exp = e->alph == ALPH_AMINO;  // per-lane scaling exponents (see wave_kernels.cuh)
-#if WITCH_WAVE_PAIR
-    if (!ALIGN && !lane_exp && !d_dbg_fwd && !d_dbg_bwd) { run_wave_pair<WITCH_PAIR_WARPS, WITCH_PAIR_MINB, 3>(e, q, buckets, d_envsc, d_domcorr, st); return; }
-#endif
     if (ALIGN) { if (lane_exp) run_wave_c<true, 8, 4, 2, 3, true>(WV_ARGS); else run_wave_c<true, 8, 4, 2, 3, false>(WV_ARGS); }
     else { if (lane_exp) run_wave_c<false, 8, WITCH_ENV_WARPS, WITCH_ENV_MINB, 3, true>(WV_ARGS); else run_wave_c<false, 8, WITCH_ENV_WARPS, WITCH_ENV_MINB, 3, false>(WV_ARGS); }
 #undef WV_ARGS
 }
 
+// Host-built work list (align stage, debug hooks: the pairs come from the caller as host arrays): bucket by length class
+// and model-size class, order each bucket by (model rank, longer first) with two stable counting passes, cut groups,
+// upload everything into handle-owned buffers.
 template <bool ALIGN>
-static void run_wave(witch_ehmm *e, witch_queries *q, const std::vector<WaveItem> &items, float *d_envsc, float *d_domcorr,
-                     int *d_cols, const long long *d_coloff, float *d_dbg_fwd, float *d_dbg_bwd, cudaStream_t st) {
-    if (items.empty()) return;
-    std::vector<WaveBucket> buckets = bucketize_items(e, items);
-    run_wave<ALIGN>(e, q, buckets, d_envsc, d_domcorr, d_cols, d_coloff, d_dbg_fwd, d_dbg_bwd, st);
+static void run_wave_host_items(witch_ehmm *e, witch_queries *q, const std::vector<WaveItem> &in, float *d_envsc, float *d_domcorr,
+                                int *d_cols, const long long *d_coloff, float *d_dbg_fwd, float *d_dbg_bwd, cudaStream_t st) {
+    if (in.empty()) return;
+    const int GW = 4;   // warps per CTA of every wave kernel instantiation used above
+    std::vector<std::vector<WaveItem>> buckets(WL_BUCKETS);
+    for (auto &it : in) buckets[wl_bucket(it.Ls, e->M[it.h])].push_back(it);
+    std::vector<WaveItem> items;
+    std::vector<int> gfirst, grange(2 * 16, 0);
+    std::vector<WaveLaunch> launches;
+    items.reserve(in.size());
+    for (int b = 0; b < WL_BUCKETS; b++) {
+        auto &bk = buckets[b];
+        if (bk.empty()) continue;
+        int Lcap = 0;
+        for (auto &it : bk) Lcap = std::max(Lcap, it.Ls);
+        std::vector<WaveItem> tmp(bk.size());
+        std::vector<size_t> cnt((size_t)Lcap + 2, 0);
+        for (auto &it : bk) cnt[Lcap - it.Ls + 1]++;                 // key 2: Ls descending
+        for (size_t k = 1; k < cnt.size(); k++) cnt[k] += cnt[k - 1];
+        for (auto &it : bk) tmp[cnt[Lcap - it.Ls]++] = it;
+        cnt.assign((size_t)e->H + 1, 0);
+        for (auto &it : tmp) cnt[e->hrank[it.h] + 1]++;              // key 1: model rank
+        for (size_t k = 1; k < cnt.size(); k++) cnt[k] += cnt[k - 1];
+        for (auto &it : tmp) bk[cnt[e->hrank[it.h]]++] = it;
+        WaveLaunch L;
+        L.Lcap = Lcap; L.nitems = (long long)bk.size();
+        grange[2 * b] = (int)gfirst.size();
+        const size_t base = items.size();
+        for (size_t i = 0; i < bk.size();) {
+            size_t j = i;
+            while (j < bk.size() && bk[j].h == bk[i].h && j - i < (size_t)GW) j++;
+            gfirst.push_back((int)(base + i));
+            i = j;
+        }
+        grange[2 * b + 1] = (int)gfirst.size();
+        for (auto &it : bk) { L.maxM = std::max(L.maxM, e->M[it.h]); L.cells += (double)it.Ls * e->M[it.h]; items.push_back(it); }
+        L.item_end = (int)items.size();
+        L.grange = (const int *)(intptr_t)b;   // bucket id for now: the device pointers exist after the upload below
+        launches.push_back(L);
+    }
+    // (the previous call's launches may still read these buffers: reuse is ordered by the stream, growth synchronises)
+    if (items.size() > e->items.n || gfirst.size() > e->group_first.n) CUDA_TRY(cudaStreamSynchronize(st));
+    e->items.upload(items, st);
+    e->group_first.upload(gfirst, st);
+    e->grange.upload(grange, st);
+    e->counter.alloc(64);
+    CUDA_TRY(cudaMemsetAsync(e->counter.p, 0, 64 * sizeof(unsigned), st));
+    for (auto &L : launches) {
+        const int b = (int)(intptr_t)L.grange;
+        L.grange = e->grange.p + 2 * b;
+        L.counter = e->counter.p + b;
+    }
+    run_wave<ALIGN>(e, q, e->items.p, e->group_first.p, launches, d_envsc, d_domcorr, d_cols, d_coloff, d_dbg_fwd, d_dbg_bwd, st);
 }
 
 static void check_handles(witch_ehmm *e, witch_queries *q) {
     if (!e || !q) throw std::invalid_argument("null handle");
     if (e->alph != q->alph) throw std::invalid_argument("queries were digitised for another alphabet");
+    if (e->device != q->device) throw std::invalid_argument("queries live on another device than the eHMM");
     CUDA_TRY(cudaSetDevice(e->device));
+}
+
+// exclusive sum / key-value sort / running maximum on the device (CUB; the host simulation build substitutes loops)
+static void dev_exclusive_sum(witch_ehmm *e, const int *in, int *out, long long n, cudaStream_t st) {
+#ifdef WITCH_HOST_SIM
+    int acc = 0;
+    for (long long i = 0; i < n; i++) { const int v = in[i]; out[i] = acc; acc += v; }
+#else
+    size_t tmp = 0;
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, out, n, st));
+    e->cubtmp.alloc(tmp);
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(e->cubtmp.p, tmp, in, out, n, st));
+#endif
+}
+static void dev_inclusive_max(witch_ehmm *e, const int *in, int *out, long long n, cudaStream_t st) {
+#ifdef WITCH_HOST_SIM
+    int acc = 0;
+    for (long long i = 0; i < n; i++) { acc = std::max(acc, in[i]); out[i] = acc; }
+#else
+    size_t tmp = 0;
+    CUDA_TRY(cub::DeviceScan::InclusiveScan(nullptr, tmp, in, out, cub::Max(), n, st));
+    e->cubtmp.alloc(tmp);
+    CUDA_TRY(cub::DeviceScan::InclusiveScan(e->cubtmp.p, tmp, in, out, cub::Max(), n, st));
+#endif
+}
+static void dev_sort_items(witch_ehmm *e, const unsigned long long *kin, unsigned long long *kout, const WaveItem *vin, WaveItem *vout,
+                           long long n, cudaStream_t st) {
+#ifdef WITCH_HOST_SIM
+    std::vector<long long> ix(n);
+    std::iota(ix.begin(), ix.end(), 0);
+    std::stable_sort(ix.begin(), ix.end(), [&](long long a, long long b) { return kin[a] < kin[b]; });
+    for (long long i = 0; i < n; i++) { kout[i] = kin[ix[i]]; vout[i] = vin[ix[i]]; }
+#else
+    size_t tmp = 0;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp, kin, kout, vin, vout, n, 0, 36, st));
+    e->cubtmp.alloc(tmp);
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(e->cubtmp.p, tmp, kin, kout, vin, vout, n, 0, 36, st));
+#endif
+}
+
+// The multi-domain branch for the nmd flagged regions listed in e->mdregs -> e->mdout.
+static void run_md(witch_ehmm *e, witch_queries *q, int nmd, cudaStream_t st) {
+    if (nmd <= 0) return;
+    const int Lcap = q->maxlen, Qcap = e->maxQ;
+    int Mcap = 0;
+    for (int m : e->M) Mcap = std::max(Mcap, m);
+    const int nsp_cap = 4096;
+    const MdLayout lay = md_layout(Lcap, Qcap, Mcap, nsp_cap);
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    const double budget = std::min<double>(48.0e9, 0.4 * (double)(free_b + e->mdbytes.n));
+    int occ = 1;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, md_region_kernel, MD_WARPS * 32, 0));
+    long long grid = std::min<long long>((nmd + MD_WARPS - 1) / MD_WARPS, (long long)e->num_sms * std::max(occ, 1));
+    grid = std::max<long long>(1, std::min<long long>(grid, (long long)(budget / ((double)lay.total * MD_WARPS))));
+    if ((double)lay.total * MD_WARPS > budget) throw std::runtime_error("not enough device memory for the multi-domain scratch");
+    const size_t need = (size_t)grid * MD_WARPS * lay.total;
+    if (need > e->mdbytes.n) { CUDA_TRY(cudaStreamSynchronize(st)); e->mdbytes.alloc(need); }
+    MdWork W;
+    W.regions = e->mdregs.p; W.nregions = nmd; W.counter = e->counter.p + 32; W.scratch = (char *)e->mdbytes.p;
+    W.slot_bytes = lay.total; W.Lcap = Lcap; W.Qcap = Qcap; W.Mcap = Mcap; W.nsp_cap = nsp_cap; W.out = e->mdout.p;
+    ScopedTimer tm(3, st, 0.0);
+    WITCH_LAUNCH(md_region_kernel, (int)grid, MD_WARPS * 32, 0, st)(e->view(), q->view(), W);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
 }
 
 extern "C" int witch_score_dev(witch_ehmm *e, witch_queries *q, float *d_scores, uint8_t *d_reported, float *d_pre,
@@ -216,42 +235,80 @@ extern "C" int witch_score_dev(witch_ehmm *e, witch_queries *q, float *d_scores,
         cudaStream_t st = (cudaStream_t)stream;
         const int nq = q->n, H = e->H;
         if (nq == 0) return WITCH_OK;
+        const long long np = (long long)nq * H;
+        if (np * (long long)MAX_ENV >= (1LL << 31)) return fail(WITCH_ERR_LIMIT, "more than 2^31 envelope slots: split the query set");
         std::vector<int> qs(nq), hs(H);
         std::iota(qs.begin(), qs.end(), 0);
         std::iota(hs.begin(), hs.end(), 0);
         HostClock hc;
         run_parser(e, q, qs, hs, nullptr, st);
         hc.lap("parser");
-        // envelope list -> wave items (host side)
-        std::vector<PairParse> parse((size_t)nq * H);
-        CUDA_TRY(cudaMemcpyAsync(parse.data(), e->parse.p, parse.size() * sizeof(PairParse), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
-        hc.lap("parse D2H");
-        // work list of the envelope stage; env_base[p] = first output slot of pair p
-        std::vector<int> env_base((size_t)nq * H, 0);
-        std::vector<WaveItem> items;
-        for (int qi = 0; qi < nq; qi++)
-            for (int h = 0; h < H; h++) {
-                const PairParse &pp = parse[(size_t)qi * H + h];
-                env_base[(size_t)qi * H + h] = (int)items.size();
-                for (int k = 0; k < pp.nenv; k++) {
-                    WaveItem it;
-                    it.q = qi; it.h = h; it.i0 = pp.env_i[k]; it.Ls = pp.env_j[k] - pp.env_i[k] + 1;
-                    it.pair = (int)items.size();
-                    items.push_back(it);
-                }
+        // ---- region counts, scans, totals: the only host-visible numbers are the sizes of the two lists ----
+        const unsigned nb = (unsigned)((np + 255) / 256);
+        e->cntA.alloc(np); e->cntB.alloc(np); e->baseA.alloc(np); e->baseB.alloc(np); e->desc.alloc(1);
+        e->counter.alloc(64);
+        CUDA_TRY(cudaMemsetAsync(e->counter.p, 0, 64 * sizeof(unsigned), st));
+        CUDA_TRY(cudaMemsetAsync(e->desc.p, 0, sizeof(WlDesc), st));
+        WITCH_LAUNCH(region_count_kernel, nb, 256, 0, st)(e->parse.p, np, e->cntA.p, e->cntB.p);
+        dev_exclusive_sum(e, e->cntA.p, e->baseA.p, np, st);
+        dev_exclusive_sum(e, e->cntB.p, e->baseB.p, np, st);
+        WITCH_LAUNCH(scan_totals_kernel, 1, 32, 0, st)(e->cntA.p, e->baseA.p, e->cntB.p, e->baseB.p, np, e->desc.p);
+        g_launches += 2;
+        CUDA_TRY(cudaMemcpyAsync(e->hdesc, e->desc.p, sizeof(WlDesc), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));   // sizing step 1: how many single-domain / multi-domain regions
+        const int nA = e->hdesc->totals[0], nmd = e->hdesc->totals[1];
+        const long long NI = (long long)nA + (long long)nmd * MD_MAXC;
+        hc.lap("region lists");
+        e->f1.alloc((size_t)NI + 1); e->f2.alloc((size_t)NI + 1);
+        e->items.alloc((size_t)NI + 1); e->items2.alloc((size_t)NI + 1); e->keys.alloc((size_t)NI + 1); e->keys2.alloc((size_t)NI + 1);
+        e->mdregs.alloc((size_t)nmd + 1); e->mdout.alloc((size_t)nmd + 1);
+        if (nmd > 0) {
+            WITCH_LAUNCH(md_list_kernel, nb, 256, 0, st)(e->parse.p, np, H, e->baseB.p, e->mdregs.p);
+            g_launches++;
+            run_md(e, q, nmd, st);
+            hc.lap("multi-domain branch");
+        }
+        if (NI > 0) {
+            WITCH_LAUNCH(items_sd_kernel, nb, 256, 0, st)(e->parse.p, np, H, e->baseA.p, e->dhrank.p, e->dM.p, e->items.p, e->keys.p, e->desc.p);
+            g_launches++;
+            if (nmd > 0) {
+                WITCH_LAUNCH(items_md_kernel, (unsigned)((nmd * MD_MAXC + 255) / 256), 256, 0, st)(e->mdregs.p, e->mdout.p, nmd, nA, e->dhrank.p,
+                                                                                            e->dM.p, e->items.p, e->keys.p, e->desc.p);
+                g_launches++;
             }
-        const size_t nitems = items.size();
-        hc.lap("build items");
-        e->f1.alloc(nitems + 1);
-        e->f2.alloc(nitems + 1);
-        e->i3.upload(env_base, st);
-        hc.lap("upload env_base");
-        run_wave<false>(e, q, items, e->f1.p, e->f2.p, nullptr, nullptr, nullptr, nullptr, st);
-        hc.lap("run_wave (all buckets)");
-        const long long np = (long long)nq * H;
-        WITCH_LAUNCH(finalize_scores_kernel, (unsigned)((np + 255) / 256), 256, 0, st)(e->parse.p, q->dlen.p, nq, H, e->i3.p, e->f1.p,
-                                                                           e->f2.p, d_scores, d_reported, d_pre, d_flags);
+            dev_sort_items(e, e->keys.p, e->keys2.p, e->items.p, e->items2.p, NI, st);
+            e->runhead.alloc((size_t)NI); e->runstart.alloc((size_t)NI); e->gflag.alloc((size_t)NI); e->gid.alloc((size_t)NI);
+            e->group_first.alloc((size_t)NI + 1); e->grange.alloc(32);
+            const unsigned nbi = (unsigned)((NI + 255) / 256);
+            CUDA_TRY(cudaMemsetAsync(e->grange.p, 0, 32 * sizeof(int), st));
+            WITCH_LAUNCH(group_head_kernel, nbi, 256, 0, st)(e->keys2.p, (int)NI, e->runhead.p);
+            dev_inclusive_max(e, e->runhead.p, e->runstart.p, NI, st);
+            WITCH_LAUNCH(group_flag_kernel, nbi, 256, 0, st)(e->keys2.p, e->runstart.p, (int)NI, WITCH_ENV_WARPS, e->gflag.p);
+            dev_exclusive_sum(e, e->gflag.p, e->gid.p, NI, st);
+            WITCH_LAUNCH(group_scatter_kernel, nbi, 256, 0, st)(e->keys2.p, e->gflag.p, e->gid.p, (int)NI, e->group_first.p, e->grange.p);
+            g_launches += 3;
+            CUDA_TRY(cudaMemcpyAsync(e->hdesc, e->desc.p, sizeof(WlDesc), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));   // sizing step 2: items / longest envelope of every bucket
+            hc.lap("work list (device)");
+            std::vector<WaveLaunch> launches;
+            int maxM_small = 0, maxM_big = 0;
+            for (int h = 0; h < H; h++) { if (e->M[h] > 13 * 256) maxM_big = std::max(maxM_big, e->M[h]); else maxM_small = std::max(maxM_small, e->M[h]); }
+            long long off = 0;
+            for (int b = 0; b < WL_BUCKETS; b++) {
+                const int cnt = e->hdesc->count[b];
+                if (cnt == 0) continue;
+                WaveLaunch L;
+                off += cnt;
+                L.item_end = (int)off; L.nitems = cnt; L.Lcap = e->hdesc->maxLs[b]; L.maxM = (b & 1) ? maxM_big : maxM_small;
+                L.cells = e->hdesc->cells[b]; L.grange = e->grange.p + 2 * b; L.counter = e->counter.p + b;
+                launches.push_back(L);
+            }
+            run_wave<false>(e, q, e->items2.p, e->group_first.p, launches, e->f1.p, e->f2.p, nullptr, nullptr, nullptr, nullptr, st);
+            hc.lap("run_wave (all buckets)");
+        }
+        WITCH_LAUNCH(finalize_scores_kernel, (unsigned)((np + 255) / 256), 256, 0, st)(e->parse.p, q->dlen.p, nq, H, e->baseA.p, e->baseB.p,
+                                                                           e->mdout.p, nA, e->f1.p, e->f2.p, d_scores, d_reported,
+                                                                           d_pre, d_flags);
         g_launches++;
         CUDA_TRY(cudaGetLastError());
         return WITCH_OK;
@@ -350,10 +407,14 @@ extern "C" int witch_align_dev(witch_ehmm *e, witch_queries *q, int n_pairs, con
         if (n_pairs == 0) return WITCH_OK;
         cudaStream_t st = (cudaStream_t)stream;
         std::vector<WaveItem> items = align_items(e, q, n_pairs, qidx, hidx);
-        std::vector<long long> co(col_offsets, col_offsets + n_pairs);
-        DevBuf<long long> dco; dco.upload(co, st);
-        run_wave<true>(e, q, items, nullptr, nullptr, d_cols, dco.p, nullptr, nullptr, st);
-        CUDA_TRY(cudaStreamSynchronize(st));
+        std::vector<long long> co(n_pairs);
+        for (int p = 0; p < n_pairs; p++) {
+            if (col_offsets[p] < 0) return fail(WITCH_ERR_ARG, "witch_align: negative column offset");
+            co[p] = col_offsets[p];
+        }
+        if ((size_t)n_pairs > e->coloff.n) CUDA_TRY(cudaStreamSynchronize(st));
+        e->coloff.upload(co, st);
+        run_wave_host_items<true>(e, q, items, nullptr, nullptr, d_cols, e->coloff.p, nullptr, nullptr, st);
         return WITCH_OK;
     } catch (const std::invalid_argument &ex) {
         return fail(WITCH_ERR_ARG, ex.what());
@@ -392,6 +453,8 @@ extern "C" int witch_debug_fwdbwd(witch_ehmm *e, witch_queries *q, int n_pairs, 
     try {
         check_handles(e, q);
         if (n_pairs <= 0 || !qidx || !hidx || !fwd_nats || !bwd_nats) return fail(WITCH_ERR_ARG, "bad arguments");
+        for (int p = 0; p < n_pairs; p++)
+            if (qidx[p] < 0 || qidx[p] >= q->n || hidx[p] < 0 || hidx[p] >= e->H) return fail(WITCH_ERR_ARG, "witch_debug_fwdbwd: pair index out of range");
         if (mode == 1) {
             // multihit parser: run per distinct (q, h) through Family S
             std::vector<int> qs(qidx, qidx + n_pairs), hs(hidx, hidx + n_pairs);
@@ -414,7 +477,8 @@ extern "C" int witch_debug_fwdbwd(witch_ehmm *e, witch_queries *q, int n_pairs, 
             df.alloc(n_pairs); db.alloc(n_pairs); d1.alloc(n_pairs); d2.alloc(n_pairs);
             CUDA_TRY(cudaMemset(df.p, 0, n_pairs * sizeof(float)));
             CUDA_TRY(cudaMemset(db.p, 0, n_pairs * sizeof(float)));
-            run_wave<false>(e, q, items, d1.p, d2.p, nullptr, nullptr, df.p, db.p, nullptr);
+            run_wave_host_items<false>(e, q, items, d1.p, d2.p, nullptr, nullptr, df.p, db.p, nullptr);
+            CUDA_TRY(cudaDeviceSynchronize());
             CUDA_TRY(cudaMemcpy(fwd_nats, df.p, n_pairs * sizeof(float), cudaMemcpyDeviceToHost));
             CUDA_TRY(cudaMemcpy(bwd_nats, db.p, n_pairs * sizeof(float), cudaMemcpyDeviceToHost));
         }

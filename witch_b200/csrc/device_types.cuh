@@ -27,6 +27,12 @@ struct DevEhmm {
     const int *stride;
     const long long *poff;
     const long long *eoff;
+    // hmmsearch's own striped float tables (hmm_profile.cpp:build_striped), read by the multi-domain branch only
+    const float *otfv;       // per HMM at otoff[h]: [(7*Q + Q)][4]
+    const float *orfv;       // per HMM at oroff[h]: [Kp][Q][4]
+    const long long *otoff;
+    const long long *oroff;
+    const int *oQ;
     int H;
     int Kp;
 };
@@ -45,7 +51,7 @@ struct DevQueries {
 struct PairParse {
     float fwd_bits;        // log2 of the multihit Forward probability (odds space)
     int nenv;              // number of envelopes (regions); 0 => pair is not reported
-    int flags;             // WITCH_FLAG_MULTIDOMAIN if any region failed the single-domain test
+    int flags;             // bit 0: some region failed the single-domain test; bit 8+r: region r did; bit 2: > MAX_ENV regions
     int env_i[MAX_ENV];    // 1-based inclusive envelope coordinates
     int env_j[MAX_ENV];
 };

@@ -3,6 +3,7 @@
 // reference's HMMER 3.1b2 binaries do with the file written at witch_msa/gcmm/algorithm.py:463-470.
 #include "hmm_profile.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -74,6 +75,88 @@ static double parse_prob(const std::string &tok) {
     if (tok == "*") return 0.0;
     return std::exp(-std::strtod(tok.c_str(), nullptr));
 }
+static double parse_raw(const std::string &tok) { return tok == "*" ? INFINITY : std::strtod(tok.c_str(), nullptr); }
+
+// exp() the way Easel's vector code evaluates it for the striped tables (Cephes-style range reduction + degree-5
+// polynomial, every operation a separate FP32 rounding): the striped parameters must round exactly like hmmsearch's.
+static float striped_expf(float x) {
+    const float x0 = x;
+    float fx = x * 1.44269502f;
+    fx = fx + 0.5f;
+    float fl = (float)(int)fx;
+    if (fx < fl) fl = fl - 1.0f;
+    const int n = (int)fl;
+    const float hi = fl * 0.693359375f, lo = fl * -2.12194440e-4f;
+    x = x - hi;
+    x = x - lo;
+    const float z = x * x;
+    static const uint32_t cbits[5] = {961571175u, 985088974u, 1007192328u, 1026206145u, 1042983594u};
+    float c[5];
+    std::memcpy(c, cbits, sizeof(c));
+    float y = c[0] * x;
+    for (int j = 1; j < 5; j++) { y = y + c[j]; y = y * x; }
+    y = y + 0.5f;
+    y = y * z;
+    y = y + x;
+    y = y + 1.0f;
+    const uint32_t pw = (uint32_t)(n + 127) << 23;
+    float p2;
+    std::memcpy(&p2, &pw, 4);
+    y = y * p2;
+    if (x0 > 88.3762588501f) return INFINITY;
+    if (x0 <= -88.3762588501f) return 0.0f;
+    return y;
+}
+
+// hmmsearch's float pipeline from the text numbers to the striped probability tables: p = expf(-x); occupancy and
+// local entry in float (the 1 - occ term in double); scores = (float)log(double); tables = striped_expf(score).
+static void build_striped(HostProfile &p, const AlphabetInfo &A, const std::vector<double> &raw_t, const std::vector<double> &raw_mat) {
+    const int M = p.M, K = A.K, Kp = A.Kp;
+    const int Q = std::max(2, (M - 1) / 4 + 1);
+    p.Q = Q;
+    std::vector<float> t((size_t)(M + 1) * 7), mat((size_t)(M + 1) * K, 0.f);
+    for (size_t z = 0; z < t.size(); z++) t[z] = std::isinf(raw_t[z]) ? 0.0f : expf((float)(-1.0 * raw_t[z]));
+    for (size_t z = (size_t)K; z < mat.size(); z++) mat[z] = std::isinf(raw_mat[z]) ? 0.0f : expf((float)(-1.0 * raw_mat[z]));
+    std::vector<float> occ(M + 2, 0.f);
+    occ[1] = t[1] + t[0];
+    for (int k = 2; k <= M; k++) {
+        const float a = occ[k - 1] * (t[(size_t)(k - 1) * 7 + 0] + t[(size_t)(k - 1) * 7 + 1]);
+        occ[k] = (float)((double)a + (1.0 - (double)occ[k - 1]) * (double)t[(size_t)(k - 1) * 7 + 5]);
+    }
+    float Z = 0.f;
+    for (int k = 1; k <= M; k++) Z += occ[k] * (float)(M - k + 1);
+    const float NEG = -INFINITY;
+    std::vector<float> tsc((size_t)(M + 1) * 8, NEG);   // [k][MM,MI,MD,IM,II,DM,DD, entry into k+1]
+    for (int k = 1; k <= M; k++) tsc[(size_t)(k - 1) * 8 + 7] = (float)std::log((double)(occ[k] / Z));
+    for (int k = 1; k < M; k++)
+        for (int x = 0; x < 7; x++) tsc[(size_t)k * 8 + x] = (float)std::log((double)t[(size_t)k * 7 + x]);
+    std::vector<float> bg(K);
+    for (int x = 0; x < K; x++) bg[x] = (float)A.bg[x];
+    p.orfv.assign((size_t)Kp * Q * 4, 0.f);
+    std::vector<float> sc(Kp);
+    for (int k = 1; k <= M; k++) {
+        for (int x = 0; x < Kp; x++) sc[x] = NEG;
+        for (int x = 0; x < K; x++) sc[x] = (float)std::log((double)mat[(size_t)k * K + x] / bg[x]);
+        for (int x = K + 1; x <= Kp - 3; x++) {
+            float num = 0.f, den = 0.f;
+            for (int m : A.degen[x]) { num += sc[m] * bg[m]; den += bg[m]; }
+            if (!A.degen[x].empty()) sc[x] = num / den;
+        }
+        const int q = (k - 1) % Q, z = (k - 1) / Q;
+        for (int x = 0; x < Kp; x++) p.orfv[((size_t)x * Q + q) * 4 + z] = striped_expf(sc[x]);
+    }
+    p.otfv.assign((size_t)8 * Q * 4, 0.f);
+    static const int src[7] = {7, 0, 3, 5, 2, 1, 4};   // BM, MM, IM, DM (from node k-1), MD, MI, II (of node k)
+    for (int q = 0; q < Q; q++)
+        for (int z = 0; z < 4; z++) {
+            const int k = q + 1 + z * Q;
+            for (int tt = 0; tt < 7; tt++) {
+                const int kb = (tt <= 3) ? k - 1 : k;
+                p.otfv[((size_t)7 * q + tt) * 4 + z] = striped_expf(kb < M ? tsc[(size_t)kb * 8 + src[tt]] : NEG);
+            }
+            p.otfv[((size_t)7 * Q + q) * 4 + z] = striped_expf(k < M ? tsc[(size_t)k * 8 + 6] : NEG);
+        }
+}
 
 static std::vector<std::string> split(const std::string &s) {
     std::vector<std::string> out;
@@ -117,18 +200,19 @@ HostProfile load_profile(const std::string &path, int /*pad_to*/) {
     tok = split(line);
     if (tok.size() < 7) throw std::runtime_error("bad node-0 transition line in " + path);
     std::vector<double> t((size_t)(M + 1) * 7, 0.0), mat((size_t)(M + 1) * K, 0.0);
-    for (int x = 0; x < 7; x++) t[x] = parse_prob(tok[x]);
+    std::vector<double> raw_t((size_t)(M + 1) * 7, INFINITY), raw_mat((size_t)(M + 1) * K, INFINITY);
+    for (int x = 0; x < 7; x++) { t[x] = parse_prob(tok[x]); raw_t[x] = parse_raw(tok[x]); }
     for (int k = 1; k <= M; k++) {
         if (!std::getline(in, line)) throw std::runtime_error("truncated HMM file " + path);
         tok = split(line);
         if ((int)tok.size() < K + 1 || std::atoi(tok[0].c_str()) != k)
             throw std::runtime_error("bad match line at node " + std::to_string(k) + " in " + path);
-        for (int x = 0; x < K; x++) mat[(size_t)k * K + x] = parse_prob(tok[1 + x]);
+        for (int x = 0; x < K; x++) { mat[(size_t)k * K + x] = parse_prob(tok[1 + x]); raw_mat[(size_t)k * K + x] = parse_raw(tok[1 + x]); }
         std::getline(in, line);  // insert emissions: ignored, insert odds are hard-wired to 1
         if (!std::getline(in, line)) throw std::runtime_error("truncated HMM file " + path);
         tok = split(line);
         if (tok.size() < 7) throw std::runtime_error("bad transition line at node " + std::to_string(k));
-        for (int x = 0; x < 7; x++) t[(size_t)k * 7 + x] = parse_prob(tok[x]);
+        for (int x = 0; x < 7; x++) { t[(size_t)k * 7 + x] = parse_prob(tok[x]); raw_t[(size_t)k * 7 + x] = parse_raw(tok[x]); }
     }
     // occupancy -> local entry distribution
     std::vector<double> occ(M + 1, 0.0);
@@ -165,6 +249,7 @@ HostProfile load_profile(const std::string &path, int /*pad_to*/) {
         }
         for (int x = 0; x < Kp; x++) p.emis[(size_t)x * stride + k] = (float)std::exp(sc[x]);
     }
+    build_striped(p, A, raw_t, raw_mat);
     return p;
 }
 

@@ -32,6 +32,12 @@ struct HostProfile {
     std::vector<float> gD;               // gD[k] = 1 + tDD[k]*gD[k+1]: Backward D_k response to a unit E exit (model constant)
     std::vector<float> emis;             // [Kp][stride] match odds ratios; insert odds == 1
     int stride = 0;                      // row stride of emis (= padded length)
+    // The same model as hmmsearch's own float "optimized profile" (4-way striped vectors, Q = max(2, (M-1)/4+1) per
+    // row), value for value: used only by the multi-domain branch of the domain definition (md_kernel.cuh), whose
+    // sampled traces depend on FP32 comparisons and therefore on HMMER's exact parameter rounding.
+    int Q = 0;
+    std::vector<float> otfv;             // [(7*Q + Q)][4]: BM,MM,IM,DM,MD,MI,II per q, then the Q DD vectors
+    std::vector<float> orfv;             // [Kp][Q][4] match odds
 };
 
 // Parse + configure. Throws std::runtime_error with a message on malformed input.

@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser_kernel(DevEhmm E, DevQue
                             mx = fmaxf(mx, fminf(dET[zz] - eb, bj - dBT[zz - 1]));
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                        if (mx >= rt3) flags |= 1;
+                        if (mx >= rt3) flags |= 1 | (nenv < MAX_ENV ? (256 << nenv) : 0);   // bit 8+r: region r is multi-domain
                         if (nenv < MAX_ENV && lane == 0) { res->env_i[nenv] = i0; res->env_j[nenv] = j; }
                         nenv++;
                         i0 = -1; trig = 0;

@@ -2,6 +2,7 @@
 // adjusted-bitscore weights + top-k (reference witch_msa/gcmm/weighting.py:58-74, gcmm/loader.py:318-330).
 #pragma once
 #include "device_types.cuh"
+#include "md_kernel.cuh"
 
 namespace witch {
 
@@ -12,10 +13,13 @@ __device__ __forceinline__ float log1p_omega_exp(float x) {
     return y > 20.f ? y : log1pf(expf(y));
 }
 
-// One thread per (query, HMM) pair.
+// One thread per (query, HMM) pair. Regions that went through the multi-domain branch (md_kernel.cuh) contribute the
+// trace-derived null2 of the whole region to the sequence bias and one envelope per cluster to the reconstruction score.
 __global__ void finalize_scores_kernel(const PairParse *parse, const int *qlen, int nq, int H,
-                                       const int *env_base,      // [nq*H] first envelope slot of the pair
-                                       const float *envsc, const float *domcorr,  // per envelope slot (nats)
+                                       const int *baseA,         // [nq*H] first wave slot of the pair's single-domain regions
+                                       const int *baseB,         // [nq*H] first multi-domain region record of the pair
+                                       const MdOut *mdout, int nA,
+                                       const float *envsc, const float *domcorr,  // per wave slot (nats)
                                        float *scores, uint8_t *reported, float *pre, uint8_t *flags) {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= (long long)nq * H) return;
@@ -33,21 +37,37 @@ __global__ void finalize_scores_kernel(const PairParse *parse, const int *qlen, 
         prev = (fwd - nullsc) / LN2;
         if (pp.nenv > 0) {
             float sb = 0.f, S = 0.f, corr = 0.f;
-            int Ld = 0;
-            const int b = env_base[p];
-            for (int e = 0; e < pp.nenv; e++) {
-                const float dc = domcorr[b + e], es = envsc[b + e];
-                sb += dc;
-                if (es - dc > 0.f) { S += es; Ld += pp.env_j[e] - pp.env_i[e] + 1; corr += dc; }
+            int Ld = 0, nenvelopes = 0;
+            int a = baseA[p], m = baseB[p];
+            for (int r = 0; r < pp.nenv; r++) {
+                if (pp.flags >> (8 + r) & 1) {
+                    const MdOut &o = mdout[m];
+                    sb += o.regcorr;
+                    for (int c = 0; c < o.nclust; c++) {
+                        const float dc = o.ccorr[c], es = envsc[nA + m * MD_MAXC + c];
+                        if (es - dc > 0.f) { S += es; Ld += o.cj[c] - o.ci[c] + 1; corr += dc; }
+                    }
+                    nenvelopes += o.nclust;
+                    fl |= o.flags & 4;
+                    m++;
+                } else {
+                    const float dc = domcorr[a], es = envsc[a];
+                    sb += dc;
+                    if (es - dc > 0.f) { S += es; Ld += pp.env_j[r] - pp.env_i[r] + 1; corr += dc; }
+                    nenvelopes++;
+                    a++;
+                }
             }
-            const float seqbias = log1p_omega_exp(sb);
-            float seq = (fwd - (nullsc + seqbias)) / LN2;
-            const float b2 = log1p_omega_exp(corr);
-            float sum = S + (L - (float)Ld) * logf(L / (L + 3.0f));
-            sum = (sum - (nullsc + b2)) / LN2;
-            if (Ld > 0 && sum > seq) { seq = sum; fl |= 2; }
-            score = seq;
-            rep = 1;
+            if (nenvelopes > 0) {   // (a multi-domain region whose traces give no cluster leaves nothing to report)
+                const float seqbias = log1p_omega_exp(sb);
+                float seq = (fwd - (nullsc + seqbias)) / LN2;
+                const float b2 = log1p_omega_exp(corr);
+                float sum = S + (L - (float)Ld) * logf(L / (L + 3.0f));
+                sum = (sum - (nullsc + b2)) / LN2;
+                if (Ld > 0 && sum > seq) { seq = sum; fl |= 2; }
+                score = seq;
+                rep = 1;
+            }
         }
     }
     scores[p] = score;

@@ -24,10 +24,10 @@ struct WaveItem {
 };
 
 struct WaveWork {
-    const WaveItem *items;
-    const int *group_first;  // groups of consecutive items sharing one HMM (one CTA processes a group)
-    const int *group_count;
-    int ngroups;
+    const WaveItem *items;   // sorted: items of one HMM contiguous
+    const int *group_first;  // first item of every group (a group = up to WAVE_WARPS consecutive items of one HMM; one CTA each)
+    const int *grange;       // DEVICE pair {first group, end group} of this launch (the lists are built on the device)
+    int item_end;            // items of this launch end here (a group never crosses it)
     unsigned *counter;
     // per-warp-slot scratch
     char *scratch;
@@ -257,12 +257,14 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32, MINB) wave_kernel(DevEhmm E, 
     int loaded_h = -1, Mstr = 0;
     for (;;) {
         __syncthreads();
-        if (threadIdx.x == 0) s_group = (int)atomicAdd(Wk.counter, 1u);
+        if (threadIdx.x == 0) s_group = Wk.grange[0] + (int)atomicAdd(Wk.counter, 1u);
         __syncthreads();
         const int grp = s_group;
-        if (grp >= Wk.ngroups) break;
-        const int gfirst = Wk.group_first[grp], gcount = Wk.group_count[grp];
+        if (grp >= Wk.grange[1]) break;
+        const int gfirst = Wk.group_first[grp];
         const int h = Wk.items[gfirst].h;
+        int gcount = 1;   // consecutive items of the same HMM, at most one per warp
+        while (gcount < WAVE_WARPS && gfirst + gcount < Wk.item_end && Wk.items[gfirst + gcount].h == h) gcount++;
         const int Mh = E.M[h];
         const int nstrips = (Mh + SW - 1) / SW;
         if (h != loaded_h) {

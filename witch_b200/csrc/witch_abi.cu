@@ -8,27 +8,21 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <numeric>
 #include <stdexcept>
 #include <string>
 #include <vector>
+#ifndef WITCH_HOST_SIM
+#include <cub/cub.cuh>
+#endif
 
 #include "device_types.cuh"
 #include "hmm_profile.h"
 #include "parser_kernel.cuh"
 #include "wave_kernels.cuh"
-#ifndef WITCH_WAVE_PAIR
-#define WITCH_WAVE_PAIR 0   // 1: envelope pass with two items per warp and packed f32x2 arithmetic (experimental)
-#endif
-#ifndef WITCH_PAIR_WARPS
-#define WITCH_PAIR_WARPS 4
-#endif
-#ifndef WITCH_PAIR_MINB
-#define WITCH_PAIR_MINB 3
-#endif
-#if WITCH_WAVE_PAIR
-#include "wave_pair_kernel.cuh"
-#endif
+#include "md_kernel.cuh"
+#include "worklist_kernels.cuh"
 #include "post_kernels.cuh"
 #include "graph_kernel.cuh"
 #include "merge_kernel.cuh"
@@ -38,9 +32,14 @@ using namespace witch;
 // ----------------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
 static std::atomic<uint64_t> g_launches{0};
-static bool g_prof = false;
+static std::atomic<bool> g_prof{false};
 struct ProfAcc { double ms = 0, cells = 0; uint64_t launches = 0; };
-static ProfAcc g_acc[3];
+static ProfAcc g_acc[4];   // 0 parser, 1 envelope, 2 align, 3 multi-domain branch
+// Timed launches leave a pair of CUDA events behind; they are resolved (cudaEventElapsedTime) when the numbers are read,
+// so profiling adds no synchronisation to the stage calls.
+struct ProfPending { cudaEvent_t a, b; int which; double cells; uint64_t launches; };
+static std::vector<ProfPending> g_pending;
+static std::mutex g_prof_mu;
 
 static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 #define CUDA_TRY(x)                                                                                          \
@@ -50,7 +49,7 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
             throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #x);      \
     } while (0)
 
-struct ScopedTimer {  // CUDA-event timing of a group of launches on `st` (only when profiling is enabled)
+struct ScopedTimer {  // CUDA-event timing of a group of launches on `st` (only when profiling is enabled); never synchronises
     cudaEvent_t a = nullptr, b = nullptr;
     cudaStream_t st;
     int which;
@@ -58,18 +57,26 @@ struct ScopedTimer {  // CUDA-event timing of a group of launches on `st` (only 
     uint64_t n0;
     ScopedTimer(int which_, cudaStream_t st_, double cells_) : st(st_), which(which_), cells(cells_) {
         n0 = g_launches.load();
-        if (g_prof) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
+        if (g_prof.load()) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
     }
     ~ScopedTimer() {
-        if (!g_prof || !a) return;
+        if (!a) return;
         cudaEventRecord(b, st);
-        cudaEventSynchronize(b);
-        float ms = 0;
-        cudaEventElapsedTime(&ms, a, b);
-        g_acc[which].ms += ms; g_acc[which].cells += cells; g_acc[which].launches += g_launches.load() - n0;
-        cudaEventDestroy(a); cudaEventDestroy(b);
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        g_pending.push_back({a, b, which, cells, g_launches.load() - n0});
     }
 };
+static void prof_resolve() {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto &p : g_pending) {
+        float ms = 0;
+        if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            g_acc[p.which].ms += ms; g_acc[p.which].cells += p.cells; g_acc[p.which].launches += p.launches;
+        }
+        cudaEventDestroy(p.a); cudaEventDestroy(p.b);
+    }
+    g_pending.clear();
+}
 
 template <typename T>
 struct DevBuf {
@@ -93,19 +100,30 @@ struct witch_ehmm {
     int device = 0, H = 0, alph = 0, Kp = 0, num_sms = 148;
     std::vector<int> M, nseq, stride;
     std::vector<long long> poff, eoff;
-    DevBuf<float> tMM, tMI, tMD, tIM, tII, tDM, tDD, entry, gD, emis;
-    DevBuf<int> dM, dstride, dnseq;
-    DevBuf<long long> dpoff, deoff;
-    // reusable workspaces
+    std::vector<int> hrank;   // launch order of the HMMs: longer models first (stable)
+    int maxQ = 0;
+    DevBuf<float> tMM, tMI, tMD, tIM, tII, tDM, tDD, entry, gD, emis, otfv, orfv;
+    DevBuf<int> dM, dstride, dnseq, doQ, dhrank;
+    DevBuf<long long> dpoff, deoff, dotoff, doroff;
+    // reusable workspaces (owned by the handle: stage calls neither allocate nor free once they have grown)
     DevBuf<float> scratch, f1, f2;
     DevBuf<unsigned> counter;
-    DevBuf<int> i1, i2, i3;
+    DevBuf<int> i1, i2, cntA, cntB, baseA, baseB, runhead, runstart, gflag, gid, group_first, grange;
     DevBuf<PairParse> parse;
-    DevBuf<uint8_t> bytes;
+    DevBuf<uint8_t> bytes, mdbytes, cubtmp;
+    DevBuf<unsigned long long> keys, keys2;
+    DevBuf<WaveItem> items, items2;
+    DevBuf<MdRegion> mdregs;
+    DevBuf<MdOut> mdout;
+    DevBuf<WlDesc> desc;
+    DevBuf<long long> coloff;
+    WlDesc *hdesc = nullptr;   // pinned host copy of the work-list descriptor
+    ~witch_ehmm() { if (hdesc) cudaFreeHost(hdesc); }
     DevEhmm view() const {
         DevEhmm v;
         v.tMM = tMM.p; v.tMI = tMI.p; v.tMD = tMD.p; v.tIM = tIM.p; v.tII = tII.p; v.tDM = tDM.p; v.tDD = tDD.p;
         v.entry = entry.p; v.gD = gD.p; v.emis = emis.p; v.M = dM.p; v.stride = dstride.p; v.poff = dpoff.p; v.eoff = deoff.p;
+        v.otfv = otfv.p; v.orfv = orfv.p; v.otoff = dotoff.p; v.oroff = doroff.p; v.oQ = doQ.p;
         v.H = H; v.Kp = Kp;
         return v;
     }
@@ -138,10 +156,11 @@ extern "C" int witch_device_count(void) {
     return n;
 }
 extern "C" uint64_t witch_kernel_launches(void) { return g_launches.load(); }
-extern "C" void witch_prof_enable(int on) { g_prof = on != 0; }
-extern "C" void witch_prof_reset(void) { for (auto &a : g_acc) a = ProfAcc(); }
+extern "C" void witch_prof_enable(int on) { g_prof.store(on != 0); }
+extern "C" void witch_prof_reset(void) { prof_resolve(); for (auto &a : g_acc) a = ProfAcc(); }
 extern "C" double witch_prof_get(int which, double *cells, uint64_t *launches) {
-    if (which < 0 || which > 2) return 0;
+    if (which < 0 || which > 3) return 0;
+    prof_resolve();
     if (cells) *cells = g_acc[which].cells;
     if (launches) *launches = g_acc[which].launches;
     return g_acc[which].ms;
@@ -188,6 +207,25 @@ extern "C" int witch_ehmm_create(int n_hmm, const char *const *paths, witch_ehmm
         e->emis.upload(cat(&HostProfile::emis));
         e->dM.upload(e->M); e->dstride.upload(e->stride); e->dnseq.upload(e->nseq);
         e->dpoff.upload(e->poff); e->deoff.upload(e->eoff);
+        {   // hmmsearch's striped float tables (multi-domain branch) and the launch rank of every HMM
+            std::vector<long long> otoff, oroff;
+            std::vector<int> oQ;
+            std::vector<float> tf, rf;
+            for (auto &p : ps) {
+                otoff.push_back((long long)tf.size()); oroff.push_back((long long)rf.size()); oQ.push_back(p.Q);
+                tf.insert(tf.end(), p.otfv.begin(), p.otfv.end());
+                rf.insert(rf.end(), p.orfv.begin(), p.orfv.end());
+                e->maxQ = std::max(e->maxQ, p.Q);
+            }
+            e->otfv.upload(tf); e->orfv.upload(rf); e->dotoff.upload(otoff); e->doroff.upload(oroff); e->doQ.upload(oQ);
+            std::vector<int> horder(e->H);
+            e->hrank.assign(e->H, 0);
+            std::iota(horder.begin(), horder.end(), 0);
+            std::stable_sort(horder.begin(), horder.end(), [&](int a, int b) { return e->M[a] > e->M[b]; });
+            for (int r = 0; r < e->H; r++) e->hrank[horder[r]] = r;
+            e->dhrank.upload(e->hrank);
+            CUDA_TRY(cudaMallocHost(&e->hdesc, sizeof(WlDesc)));
+        }
         CUDA_TRY(cudaDeviceSynchronize());
         *out = e;
         return WITCH_OK;
@@ -196,7 +234,11 @@ extern "C" int witch_ehmm_create(int n_hmm, const char *const *paths, witch_ehmm
         return fail(WITCH_ERR_CUDA, ex.what());
     }
 }
-extern "C" void witch_ehmm_destroy(witch_ehmm *e) { delete e; }
+extern "C" void witch_ehmm_destroy(witch_ehmm *e) {
+    if (!e) return;
+    cudaSetDevice(e->device);   // the buffers are freed on the device that owns them
+    delete e;
+}
 extern "C" int witch_ehmm_count(const witch_ehmm *e) { return e ? e->H : 0; }
 extern "C" int witch_ehmm_alphabet(const witch_ehmm *e) { return e ? e->alph : -1; }
 extern "C" int witch_ehmm_info(const witch_ehmm *e, int32_t *M, int32_t *nseq) {
@@ -211,6 +253,11 @@ extern "C" int witch_queries_create(const witch_ehmm *e, int n, const char *resi
     witch_queries *q = nullptr;
     try {
         const AlphabetInfo &A = alphabet_info(e->alph);
+        if (offsets[0] != 0) return fail(WITCH_ERR_ARG, "witch_queries_create: offsets[0] must be 0");
+        for (int i = 0; i < n; i++)
+            if (offsets[i + 1] < offsets[i]) return fail(WITCH_ERR_ARG, "witch_queries_create: offsets not monotone");
+        require_device();
+        CUDA_TRY(cudaSetDevice(e->device));   // the query set lives on the eHMM's device
         q = new witch_queries();
         q->n = n; q->alph = e->alph; q->device = e->device;
         const long long total = offsets[n];
@@ -250,7 +297,11 @@ extern "C" int witch_queries_create(const witch_ehmm *e, int n, const char *resi
         return fail(WITCH_ERR_CUDA, ex.what());
     }
 }
-extern "C" void witch_queries_destroy(witch_queries *q) { delete q; }
+extern "C" void witch_queries_destroy(witch_queries *q) {
+    if (!q) return;
+    cudaSetDevice(q->device);
+    delete q;
+}
 extern "C" int witch_queries_count(const witch_queries *q) { return q ? q->n : 0; }
 
 // ----------------------------------------------------------------------------------------------------------
