@@ -49,7 +49,7 @@ def test_directory_layout_scores_weights_checkpoint_roundtrip(tmp_path):
     assert ranked["renamed"] == [(0, 1.0), (1, 1.0), (2, 1.0)]
     assert ranked[names[4]][0] == (0, 100.0) or ranked[names[4]][0] == (0, 99.9)   # %.1f of the float32 value
     # weights.txt
-    t2w = {"a:b": ((3, 0.75), (1, 0.25)), "q": ((0, 1.0),)}
+    t2w = {"a_b": ((3, 0.75), (1, 0.25)), "q": ((0, 1.0),)}   # (the reference's reader splits at ':', so no colons in names)
     wp = str(tmp_path / "weights.txt")
     F.writeWeightsToLocal(t2w, wp)
     assert open(wp).read().splitlines()[1] == "q:((0, 1.0),)"
@@ -60,3 +60,30 @@ def test_directory_layout_scores_weights_checkpoint_roundtrip(tmp_path):
     F.writeCheckpointAlignments(cp, {"q3": "A"})
     assert gzip.open(cp, "rb").read().decode() == "q1\tac-GT\nq 2\t--ACg\nq3\tA\n"
     assert F.readCheckpointAlignments(cp) == {"q1": "ac-GT", "q 2": "--ACg", "q3": "A"}
+
+
+def test_writers_are_byte_identical_to_files_the_reference_readers_accepted(tmp_path):
+    """tests/golden/make_golden_c1.py wrote these files with formats.py and parsed them back with THE REFERENCE'S OWN
+    readHMMSearch (gcmm/loader.py:277-294), readWeightsFromLocal (gcmm/weighting.py:184-194) and
+    readOneCheckpointAlignment (gcmm/loader.py:95-111), asserting the content survives; the exact texts are pinned here."""
+    import json
+    from golden_util import GOLDEN
+    fmt = json.loads(gzip.open(os.path.join(GOLDEN, "c1", "c1_golden.json.gz")).read())["formats"]
+    gold, queries, paths = load_set("dna_small", str(tmp_path / "hmm"))
+    backbone = {"t0": "AC-GT-A", "t1": "A--GTCA"}
+    root, bb = _make_dir(tmp_path, paths[:2], [["t0", "t1"], ["t1"]], backbone)
+    i2h = F.getAlignmentSubsets(root)
+    files = F.writeHMMSearchResults(i2h, fmt["names"], np.array(fmt["scores"], dtype=np.float32), np.array(fmt["reported"], dtype=bool))
+    for i in (0, 1):
+        assert open(files[i]).read() == fmt["hmmsearch_files"][str(i)]
+        assert F.readHMMSearch(i2h[i]) == {t: [tuple(x) for x in v] for t, v in fmt["hmmsearch_parsed"][str(i)].items()}
+    wp = str(tmp_path / "w.txt")
+    order = [ln.split(":")[0] for ln in fmt["weights_file"].splitlines()]   # (the golden json is key-sorted; the file is not)
+    F.writeWeightsToLocal({t: tuple(tuple(x) for x in fmt["weights"][t]) for t in order}, wp)
+    assert open(wp).read() == fmt["weights_file"]
+    cp = str(tmp_path / "cp.txt.gz")
+    rows = fmt["checkpoint_rows"]
+    F.writeCheckpointAlignments(cp, {"SHFB": rows["SHFB"]}, append=False)
+    F.writeCheckpointAlignments(cp, {k: rows[k] for k in ("Q_b", "t\tab")}, append=True)
+    assert gzip.open(cp, "rb").read().decode() == fmt["checkpoint_text"]
+    assert F.readCheckpointAlignments(cp) == rows

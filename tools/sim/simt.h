@@ -143,6 +143,7 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
     simt::warp_sync();
     return r;
 }
+static inline long long clock64() { return 0; }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 static inline int __ffs(int x) { return __builtin_ffs(x); }

@@ -211,8 +211,11 @@ static void run_md(witch_ehmm *e, witch_queries *q, int nmd, cudaStream_t st) {
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
     const double budget = std::min<double>(48.0e9, 0.4 * (double)(free_b + e->mdbytes.n));
+    const size_t smem = (size_t)MD_WARPS * 8 * Qcap * sizeof(float);   // per warp: M and D vectors of the current row
+    if (smem > 200 * 1024) throw std::runtime_error("model too long for the multi-domain branch's row staging");
+    CUDA_TRY(cudaFuncSetAttribute(md_region_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, md_region_kernel, MD_WARPS * 32, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, md_region_kernel, MD_WARPS * 32, smem));
     long long grid = std::min<long long>((nmd + MD_WARPS - 1) / MD_WARPS, (long long)e->num_sms * std::max(occ, 1));
     grid = std::max<long long>(1, std::min<long long>(grid, (long long)(budget / ((double)lay.total * MD_WARPS))));
     if ((double)lay.total * MD_WARPS > budget) throw std::runtime_error("not enough device memory for the multi-domain scratch");
@@ -222,7 +225,7 @@ static void run_md(witch_ehmm *e, witch_queries *q, int nmd, cudaStream_t st) {
     W.regions = e->mdregs.p; W.nregions = nmd; W.counter = e->counter.p + 32; W.scratch = (char *)e->mdbytes.p;
     W.slot_bytes = lay.total; W.Lcap = Lcap; W.Qcap = Qcap; W.Mcap = Mcap; W.nsp_cap = nsp_cap; W.out = e->mdout.p;
     ScopedTimer tm(3, st, 0.0);
-    WITCH_LAUNCH(md_region_kernel, (int)grid, MD_WARPS * 32, 0, st)(e->view(), q->view(), W);
+    WITCH_LAUNCH(md_region_kernel, (int)grid, MD_WARPS * 32, smem, st)(e->view(), q->view(), W);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
 }
@@ -267,6 +270,20 @@ extern "C" int witch_score_dev(witch_ehmm *e, witch_queries *q, float *d_scores,
             g_launches++;
             run_md(e, q, nmd, st);
             hc.lap("multi-domain branch");
+            if (hc.on) {   // WITCH_TIMING: where the branch spends its time (device clock ticks per region)
+                std::vector<MdOut> mo(nmd);
+                CUDA_TRY(cudaMemcpy(mo.data(), e->mdout.p, (size_t)nmd * sizeof(MdOut), cudaMemcpyDeviceToHost));
+                double s0 = 0, s1 = 0, s2 = 0; long long m0 = 0, m1 = 0, m2 = 0, worst = 0; int wi = 0;
+                for (int i = 0; i < nmd; i++) {
+                    s0 += mo[i].clk[0]; s1 += mo[i].clk[1]; s2 += mo[i].clk[2];
+                    m0 = std::max(m0, mo[i].clk[0]); m1 = std::max(m1, mo[i].clk[1]); m2 = std::max(m2, mo[i].clk[2]);
+                    const long long tot = mo[i].clk[0] + mo[i].clk[1] + mo[i].clk[2];
+                    if (tot > worst) { worst = tot; wi = i; }
+                }
+                fprintf(stderr, "[witch timing] md regions %d: Mticks mean fwd %.1f traces %.1f cluster %.1f | max fwd %.1f traces %.1f cluster %.1f | worst region Lr %d M %d: %.1f %.1f %.1f\n",
+                        nmd, s0 / nmd / 1e6, s1 / nmd / 1e6, s2 / nmd / 1e6, m0 / 1e6, m1 / 1e6, m2 / 1e6, (int)(mo[wi].clk[3] >> 32), (int)(mo[wi].clk[3] & 0xffffffff),
+                        mo[wi].clk[0] / 1e6, mo[wi].clk[1] / 1e6, mo[wi].clk[2] / 1e6);
+            }
         }
         if (NI > 0) {
             WITCH_LAUNCH(items_sd_kernel, nb, 256, 0, st)(e->parse.p, np, H, e->baseA.p, e->dhrank.p, e->dM.p, e->items.p, e->keys.p, e->desc.p);

@@ -28,6 +28,7 @@ struct MdOut {
     float regcorr;         // sum over the region of the position-specific ln null2 (from the traces)
     int ci[MD_MAXC], cj[MD_MAXC];
     float ccorr[MD_MAXC];  // sum of ln null2 over each envelope
+    long long clk[4];      // device clock ticks spent in Forward / traces / clustering (WITCH_TIMING diagnostics), region size
 };
 struct MdWork {
     const MdRegion *regions;
@@ -39,7 +40,7 @@ struct MdWork {
     MdOut *out;
 };
 
-struct MdLayout { long long dp, xmx, acc, sp, asg, epc, total; };
+struct MdLayout { long long dp, xmx, acc, sp, asg, epc, tkb, total; };
 __host__ __device__ inline MdLayout md_layout(int Lcap, int Qcap, int Mcap, int nsp_cap) {
     MdLayout l;
     long long o = 0;
@@ -49,6 +50,7 @@ __host__ __device__ inline MdLayout md_layout(int Lcap, int Qcap, int Mcap, int 
     l.sp = o; o += (long long)nsp_cap * 5 * 4;
     l.asg = o; o += (long long)nsp_cap * 4;
     l.epc = o; o += (long long)((Lcap > Mcap ? Lcap : Mcap) + 4) * 4;
+    l.tkb = o; o += (long long)(Lcap + 4) * 4;
     l.total = (o + 255) / 256 * 256;
     return l;
 }
@@ -59,6 +61,12 @@ static inline float md_add(float a, float b) { return a + b; }
 #else
 __device__ __forceinline__ float md_mul(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float md_add(float a, float b) { return __fadd_rn(a, b); }
+#endif
+
+#ifdef WITCH_HOST_SIM
+static inline void md_prefetch(const void *) {}
+#else
+__device__ __forceinline__ void md_prefetch(const void *p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 #endif
 
 __device__ __forceinline__ unsigned md_mix3(unsigned a, unsigned b, unsigned c) {
@@ -132,6 +140,9 @@ __global__ void __launch_bounds__(MD_WARPS * 32) md_region_kernel(DevEhmm E, Dev
     int *asg = (int *)(slot + lay.asg);
     int *epc = (int *)(slot + lay.epc);
     const int K = (E.Kp == 29) ? 20 : 4;
+    WITCH_DYN_SMEM(float, md_smem);   // per warp: the current row's M and D vectors, [Qcap][4] each
+    float *sMv = md_smem + (size_t)w * 8 * W.Qcap, *sDv = sMv + (size_t)4 * W.Qcap;
+    int *tkb = (int *)(slot + lay.tkb);   // model nodes of the emitting states of the running domain
 
     for (;;) {
         int item = 0;
@@ -148,15 +159,18 @@ __global__ void __launch_bounds__(MD_WARPS * 32) md_region_kernel(DevEhmm E, Dev
         const float pmove = 3.0f / ((float)L + 3.0f), ploop = 1.0f - pmove;
         const size_t RW = (size_t)Q * 12;   // floats per row: [q][M|D|I][4]
 
+        const long long clk0 = clock64();
         // ====================== Forward over the region (multihit, length model of the whole sequence) ======================
+        // A row's M and D vectors are staged in shared memory ([q][4] each) for the serial part; the global matrix row
+        // receives the final values with coalesced stores.
         for (int c = lane; c < Q * 12; c += 32) dp[c] = 0.f;
         if (lane == 0) { xmx[0] = 0.f; xmx[1] = 1.f; xmx[2] = 0.f; xmx[3] = pmove; xmx[4] = 0.f; xmx[5] = 1.f; }
         float fN = 1.0f, fB = pmove, fJ = 0.f, fC = 0.f;
         __syncwarp();
         for (int i = 1; i <= Lr; i++) {
-            const float *rp = rfv + (size_t)Qs.symrow[rd[i - 1]] * Q * 4;
-            const float *prev = dp + (size_t)(i - 1) * RW;
-            float *cur = dp + (size_t)i * RW;
+            const float *__restrict__ rp = rfv + (size_t)Qs.symrow[rd[i - 1]] * Q * 4;
+            const float *__restrict__ prev = dp + (size_t)(i - 1) * RW;
+            float *__restrict__ cur = dp + (size_t)i * RW;
             // M and I cells: independent across (q, z)
             for (int c = lane; c < Q * 4; c += 32) {
                 const int q = c >> 2, z = c & 3;
@@ -164,32 +178,45 @@ __global__ void __launch_bounds__(MD_WARPS * 32) md_region_kernel(DevEhmm E, Dev
                 if (q > 0) { const float *v = prev + (size_t)(q - 1) * 12 + z; mpv = v[0]; dpv = v[4]; ipv = v[8]; }
                 else if (z > 0) { const float *v = prev + (size_t)(Q - 1) * 12 + z - 1; mpv = v[0]; dpv = v[4]; ipv = v[8]; }
                 else { mpv = 0.f; dpv = 0.f; ipv = 0.f; }
-                const float *tp = tfv + (size_t)q * 28 + z;
+                const float *__restrict__ tp = tfv + (size_t)q * 28 + z;
+                const float mp2 = prev[(size_t)q * 12 + z], ip2 = prev[(size_t)q * 12 + 8 + z];
                 float sv = md_mul(fB, tp[0]);
                 sv = md_add(sv, md_mul(mpv, tp[4]));
                 sv = md_add(sv, md_mul(ipv, tp[8]));
                 sv = md_add(sv, md_mul(dpv, tp[12]));
                 sv = md_mul(sv, rp[c]);
-                cur[(size_t)q * 12 + z] = sv;
+                sMv[c] = sv;
                 const float dc = md_mul(sv, tp[16]);   // M->D into the next column
-                if (q + 1 < Q) cur[(size_t)(q + 1) * 12 + 4 + z] = dc;
-                else if (z < 3) cur[4 + z + 1] = dc;      // wraps into the next stripe lane of vector 0
-                if (c == 0) cur[4] = 0.f;
-                const float mp2 = prev[(size_t)q * 12 + z], ip2 = prev[(size_t)q * 12 + 8 + z];
+                if (q + 1 < Q) sDv[c + 4] = dc;
+                else if (z < 3) sDv[z + 1] = dc;       // wraps into the next stripe lane of vector 0
+                if (c == 0) sDv[0] = 0.f;
                 cur[(size_t)q * 12 + 8 + z] = md_add(md_mul(mp2, tp[20]), md_mul(ip2, tp[24]));
             }
             __syncwarp();
-            // D->D paths and the E sum: four serial chains (one per stripe lane), exactly in HMMER's order
-            const float *td = tfv + (size_t)Q * 28 + (lane & 3);
+            // D->D paths and the E sum: serial chains per stripe lane, exactly in HMMER's order. Lanes 0-3 run the D chains,
+            // lanes 4-7 the running sum of the M cells (HMMER adds all M cells first, then the D cells, lane by lane).
+            const int z4 = lane & 3;
+            const float *__restrict__ td = tfv + (size_t)Q * 28 + z4;
             float d = 0.f, xe = 0.f;
             if (lane < 4) {
-                float *cd = cur + 4 + lane;
-                const float *cm = cur + lane;
-                for (int q = 0; q < Q; q++) {
-                    const float v = md_add(d, cd[(size_t)q * 12]);
-                    cd[(size_t)q * 12] = v;
-                    d = md_mul(v, td[(size_t)q * 4]);
-                    xe = md_add(xe, cm[(size_t)q * 12]);
+                for (int q0 = 0; q0 < Q; q0 += 8) {
+                    float in[8], t8[8];
+                    const int nq8 = min(8, Q - q0);
+#pragma unroll
+                    for (int u = 0; u < 8; u++) if (u < nq8) { in[u] = sDv[(q0 + u) * 4 + z4]; t8[u] = td[(size_t)(q0 + u) * 4]; }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) if (u < nq8) { in[u] = md_add(d, in[u]); d = md_mul(in[u], t8[u]); }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) if (u < nq8) sDv[(q0 + u) * 4 + z4] = in[u];
+                }
+            } else if (lane < 8) {
+                for (int q0 = 0; q0 < Q; q0 += 8) {
+                    float in[8];
+                    const int nq8 = min(8, Q - q0);
+#pragma unroll
+                    for (int u = 0; u < 8; u++) if (u < nq8) in[u] = sMv[(q0 + u) * 4 + z4];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) if (u < nq8) xe = md_add(xe, in[u]);
                 }
             }
             for (int j = 1; j < 4; j++) {
@@ -198,21 +225,36 @@ __global__ void __launch_bounds__(MD_WARPS * 32) md_region_kernel(DevEhmm E, Dev
                 int changed = 0;
                 if (lane < 4) {
                     d = din;
-                    float *cd = cur + 4 + lane;
-                    for (int q = 0; q < Q; q++) {
-                        const float old = cd[(size_t)q * 12];
-                        const float v = md_add(d, old);
-                        if (old < v) changed = 1;
-                        cd[(size_t)q * 12] = v;
-                        d = md_mul(d, td[(size_t)q * 4]);
+                    // (once the carried term is exactly 0 the rest of the pass changes nothing: leave it)
+                    for (int q0 = 0; q0 < Q && d != 0.f; q0 += 8) {
+                        float in[8], t8[8];
+                        const int nq8 = min(8, Q - q0);
+#pragma unroll
+                        for (int u = 0; u < 8; u++) if (u < nq8) { in[u] = sDv[(q0 + u) * 4 + z4]; t8[u] = td[(size_t)(q0 + u) * 4]; }
+#pragma unroll
+                        for (int u = 0; u < 8; u++) if (u < nq8) {
+                            const float v = md_add(d, in[u]);
+                            if (in[u] < v) changed = 1;
+                            in[u] = v;
+                            d = md_mul(d, t8[u]);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; u++) if (u < nq8) sDv[(q0 + u) * 4 + z4] = in[u];
                     }
                 }
                 const unsigned any = __ballot_sync(FULL, changed != 0);
                 if (M >= 100 && any == 0u) break;
             }
+            xe = __shfl_sync(FULL, xe, 4 + z4);   // lanes 0-3 continue the sum of their stripe lane with the D cells
             if (lane < 4) {
-                const float *cd = cur + 4 + lane;
-                for (int q = 0; q < Q; q++) xe = md_add(cd[(size_t)q * 12], xe);
+                for (int q0 = 0; q0 < Q; q0 += 8) {
+                    float in[8];
+                    const int nq8 = min(8, Q - q0);
+#pragma unroll
+                    for (int u = 0; u < 8; u++) if (u < nq8) in[u] = sDv[(q0 + u) * 4 + z4];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) if (u < nq8) xe = md_add(in[u], xe);
+                }
             }
             const float x1 = __shfl_sync(FULL, xe, 1), x2 = __shfl_sync(FULL, xe, 2), x3 = __shfl_sync(FULL, xe, 3);
             float fE = md_add(md_add(__shfl_sync(FULL, xe, 0), x1), md_add(x2, x3));
@@ -221,14 +263,23 @@ __global__ void __launch_bounds__(MD_WARPS * 32) md_region_kernel(DevEhmm E, Dev
             fN = (float)((double)ploop * (double)fN);
             fC = (float)((double)ploop * (double)fC + 0.5 * (double)fE);
             fB = (float)((double)pmove * (double)fN + (double)pmove * (double)fJ);
-            float scale = 1.0f;
-            if ((double)fE > 1.0e4) {   // sparse rescaling (warp-uniform decision)
+            float scale = 1.0f, inv = 1.0f;
+            const bool resc = (double)fE > 1.0e4;   // sparse rescaling (warp-uniform decision)
+            if (resc) {
                 const double e = (double)fE;
                 fN = (float)((double)fN / e); fC = (float)((double)fC / e); fJ = (float)((double)fJ / e); fB = (float)((double)fB / e);
-                const float inv = (float)(1.0 / e);
-                for (int c = lane; c < Q * 12; c += 32) cur[c] = md_mul(cur[c], inv);
+                inv = (float)(1.0 / e);
                 scale = fE;
                 fE = 1.0f;
+            }
+            __syncwarp();
+            // final M and D cells of the row -> global matrix (the I cells are there already)
+            for (int c = lane; c < Q * 4; c += 32) {
+                const int q = c >> 2, z = c & 3;
+                float m = sMv[c], dd = sDv[c];
+                if (resc) { m = md_mul(m, inv); dd = md_mul(dd, inv); cur[(size_t)q * 12 + 8 + z] = md_mul(cur[(size_t)q * 12 + 8 + z], inv); }
+                cur[(size_t)q * 12 + z] = m;
+                cur[(size_t)q * 12 + 4 + z] = dd;
             }
             if (lane == 0) {
                 float *x = xmx + (size_t)i * 8;
@@ -237,23 +288,106 @@ __global__ void __launch_bounds__(MD_WARPS * 32) md_region_kernel(DevEhmm E, Dev
             __syncwarp();
         }
 
+        const long long clk1 = clock64();
         // ====================== 200 stochastic traces, null2 by trace, sampled domains ======================
         for (int p = lane; p <= Lr + 1; p += 32) acc[p] = 0.f;
         unsigned rng = md_mix3(42u, 87654321u, 12345678u);
         if (rng == 0u) rng = 42u;
         int nsp = 0, oflow = 0;
         __syncwarp();
+        enum { tM = 1, tD = 2, tI = 3, tS = 4, tN = 5, tB = 6, tE = 7, tC = 8, tJ = 10 };
         for (int t = 0; t < MD_NSAMPLES; t++) {
-            int i = Lr, k = 0, s0 = 8 /* C */, ndom = 0, hi = Lr;
-            // running domain (walked backwards: E first, B last)
+            // Lane 0 walks the trace backwards on its own and calls the warp in at three kinds of events: an E state to
+            // resolve (a choice among all M/D cells of a row), a finished domain (null2 of its states, per-residue
+            // accumulation), the end of the trace. Its running domain: sqfrom..sqto, hfrom..hto, Ld emitting states whose
+            // model nodes are listed in tkb[].
+            int i = Lr, k = 0, s0 = tC, ndom = 0, hi = Lr;
             int sqto = 0, sqfrom = 0, hto = 0, hfrom = 0, Ld = 0;
-            double sums[20];
-            enum { tM = 1, tD = 2, tI = 3, tS = 4, tN = 5, tB = 6, tE = 7, tC = 8, tJ = 10 };
-            while (s0 != tS) {
-                int s1 = 0;
-                if (s0 == tE) {
+            for (;;) {
+                int ev = 0;
+                if (lane == 0) {
+                    while (ev == 0) {
+                        if (s0 == tE) { ev = 1; break; }
+                        if (s0 == tS) { ev = 3; break; }
+                        int s1;
+                        const float *x1 = xmx + (size_t)i * 8, *x0 = xmx + (size_t)(i > 0 ? i - 1 : 0) * 8;
+                        float path[4];
+                        if (s0 == tM) {
+                            k--;
+                            const int q = k % Q, r = k / Q;
+                            const float *tp = tfv + (size_t)q * 28 + r;
+                            const float *pr = dp + (size_t)(i - 1) * RW;
+                            float mp = 0.f, dd = 0.f, ip = 0.f;
+                            if (q > 0) { const float *v = pr + (size_t)(q - 1) * 12 + r; mp = v[0]; dd = v[4]; ip = v[8]; }
+                            else if (r > 0) { const float *v = pr + (size_t)(Q - 1) * 12 + r - 1; mp = v[0]; dd = v[4]; ip = v[8]; }
+                            const float xb = x0[3], t0 = tp[0], t1 = tp[4], t2 = tp[8], t3 = tp[12];
+                            // the path most likely continues on the diagonal: pull the cells of the next steps towards L1
+                            if (i >= 5) {
+#pragma unroll
+                                for (int dstep = 2; dstep <= 4; dstep += 2) {
+                                    int qd = q - 1 - dstep, rd2 = r;
+                                    if (qd < 0) { qd += Q; rd2--; }
+                                    if (rd2 >= 0) {
+                                        md_prefetch(dp + (size_t)(i - 1 - dstep) * RW + (size_t)qd * 12 + rd2);
+                                        md_prefetch(tfv + (size_t)(qd + 1 < Q ? qd + 1 : 0) * 28);
+                                    }
+                                }
+                            }
+                            path[0] = md_mul(xb, t0); path[1] = md_mul(mp, t1); path[2] = md_mul(ip, t2); path[3] = md_mul(dd, t3);
+                            const int c = md_choose(rng, path, 4);
+                            s1 = (c == 0) ? tB : (c == 1) ? tM : (c == 2) ? tI : tD;
+                            i--;
+                        } else if (s0 == tD) {
+                            k--;
+                            const int q = k % Q, r = k / Q;
+                            const float *cr = dp + (size_t)i * RW;
+                            float mp = 0.f, dd = 0.f, tmd = 0.f, tdd = 0.f;
+                            if (q > 0) {
+                                mp = cr[(size_t)(q - 1) * 12 + r]; dd = cr[(size_t)(q - 1) * 12 + 4 + r];
+                                tmd = tfv[(size_t)(q - 1) * 28 + 16 + r]; tdd = tfv[(size_t)Q * 28 + (size_t)(q - 1) * 4 + r];
+                            } else if (r > 0) {
+                                mp = cr[(size_t)(Q - 1) * 12 + r - 1]; dd = cr[(size_t)(Q - 1) * 12 + 4 + r - 1];
+                                tmd = tfv[(size_t)(Q - 1) * 28 + 16 + r - 1]; tdd = tfv[(size_t)Q * 28 + (size_t)(Q - 1) * 4 + r - 1];
+                            }
+                            path[0] = md_mul(mp, tmd); path[1] = md_mul(dd, tdd);
+                            s1 = md_choose(rng, path, 2) == 0 ? tM : tD;
+                        } else if (s0 == tI) {
+                            const int q = (k - 1) % Q, r = (k - 1) / Q;
+                            const float *pr = dp + (size_t)(i - 1) * RW + (size_t)q * 12 + r;
+                            path[0] = md_mul(pr[0], tfv[(size_t)q * 28 + 20 + r]);
+                            path[1] = md_mul(pr[8], tfv[(size_t)q * 28 + 24 + r]);
+                            s1 = md_choose(rng, path, 2) == 0 ? tM : tI;
+                            i--;
+                        } else if (s0 == tN) {
+                            s1 = (i == 0) ? tS : tN;
+                        } else if (s0 == tC) {
+                            path[0] = md_mul(ploop, x0[4]);
+                            path[1] = md_mul(md_mul(0.5f, x1[0]), x1[5]);
+                            s1 = md_choose(rng, path, 2) == 0 ? tC : tE;
+                        } else if (s0 == tJ) {
+                            path[0] = md_mul(ploop, x0[2]);
+                            path[1] = md_mul(md_mul(0.5f, x1[0]), x1[5]);
+                            s1 = md_choose(rng, path, 2) == 0 ? tJ : tE;
+                        } else {   // B
+                            path[0] = md_mul(pmove, x1[1]);
+                            path[1] = md_mul(pmove, x1[2]);
+                            s1 = md_choose(rng, path, 2) == 0 ? tN : tJ;
+                        }
+                        if (s1 == tM || s1 == tI) {   // (3.1b2 counts a residue emitted by I_k in the MATCH cell of node k)
+                            if (s1 == tM) { if (sqto == 0) { sqto = i; hto = k; } sqfrom = i; hfrom = k; }
+                            tkb[Ld++] = k;
+                        }
+                        if ((s1 == tN || s1 == tJ || s1 == tC) && s1 == s0) i--;
+                        s0 = s1;
+                        if (s1 == tB) ev = 2;
+                    }
+                }
+                ev = __shfl_sync(FULL, ev, 0);
+                if (ev == 3) break;
+                if (ev == 1) {
                     // choice among all M/D cells of row i in striped order, cooperatively: each lane sums a contiguous
                     // range of vectors, a prefix scan locates the lane that crosses the roll, that lane finds the cell
+                    i = __shfl_sync(FULL, i, 0);
                     double roll = 0.0;
                     if (lane == 0) roll = md_rand(rng);
                     roll = __shfl_sync(FULL, roll, 0);
@@ -282,98 +416,47 @@ __global__ void __launch_bounds__(MD_WARPS * 32) md_region_kernel(DevEhmm E, Dev
                         }
                         kk = __shfl_sync(FULL, kk, src); ss = __shfl_sync(FULL, ss, src);
                     }
-                    k = kk; s1 = ss;
                     // a new domain starts (seen from its end)
+                    k = kk; s0 = ss;
                     sqto = 0; sqfrom = 0; hto = 0; hfrom = 0; Ld = 0;
-                    for (int x = 0; x < K; x++) sums[x] = 0.0;
-                } else if (lane == 0) {
-                    const float *x1 = xmx + (size_t)i * 8, *x0 = xmx + (size_t)(i > 0 ? i - 1 : 0) * 8;
-                    float path[4];
-                    if (s0 == tM) {
-                        k--;
-                        const int q = k % Q, r = k / Q;
-                        const float *tp = tfv + (size_t)q * 28 + r;
-                        const float *pr = dp + (size_t)(i - 1) * RW;
-                        float mp = 0.f, dd = 0.f, ip = 0.f;
-                        if (q > 0) { const float *v = pr + (size_t)(q - 1) * 12 + r; mp = v[0]; dd = v[4]; ip = v[8]; }
-                        else if (r > 0) { const float *v = pr + (size_t)(Q - 1) * 12 + r - 1; mp = v[0]; dd = v[4]; ip = v[8]; }
-                        path[0] = md_mul(x0[3], tp[0]); path[1] = md_mul(mp, tp[4]); path[2] = md_mul(ip, tp[8]); path[3] = md_mul(dd, tp[12]);
-                        const int c = md_choose(rng, path, 4);
-                        s1 = (c == 0) ? tB : (c == 1) ? tM : (c == 2) ? tI : tD;
-                        i--;
-                    } else if (s0 == tD) {
-                        k--;
-                        const int q = k % Q, r = k / Q;
-                        const float *cr = dp + (size_t)i * RW;
-                        float mp = 0.f, dd = 0.f, tmd = 0.f, tdd = 0.f;
-                        if (q > 0) {
-                            mp = cr[(size_t)(q - 1) * 12 + r]; dd = cr[(size_t)(q - 1) * 12 + 4 + r];
-                            tmd = tfv[(size_t)(q - 1) * 28 + 16 + r]; tdd = tfv[(size_t)Q * 28 + (size_t)(q - 1) * 4 + r];
-                        } else if (r > 0) {
-                            mp = cr[(size_t)(Q - 1) * 12 + r - 1]; dd = cr[(size_t)(Q - 1) * 12 + 4 + r - 1];
-                            tmd = tfv[(size_t)(Q - 1) * 28 + 16 + r - 1]; tdd = tfv[(size_t)Q * 28 + (size_t)(Q - 1) * 4 + r - 1];
+                    if (ss == tM) { sqto = i; hto = kk; sqfrom = i; hfrom = kk; if (lane == 0) tkb[0] = kk; Ld = 1; }
+                    continue;
+                }
+                // ev == 2: domain sqfrom..sqto complete: null2 odds of its states, accumulated per residue
+                sqfrom = __shfl_sync(FULL, sqfrom, 0); sqto = __shfl_sync(FULL, sqto, 0);
+                hfrom = __shfl_sync(FULL, hfrom, 0); hto = __shfl_sync(FULL, hto, 0); Ld = __shfl_sync(FULL, Ld, 0);
+                __syncwarp();
+                {
+                    const float nrm = (float)(1.0 / (double)(float)Ld);
+                    for (int x = 0; x < K; x++) {
+                        double sx = 0.0;
+                        for (int z = lane; z < Ld; z += 32) {
+                            const int kz = tkb[z] - 1;
+                            sx += (double)rfv[((size_t)x * Q + (kz % Q)) * 4 + kz / Q];
                         }
-                        path[0] = md_mul(mp, tmd); path[1] = md_mul(dd, tdd);
-                        s1 = md_choose(rng, path, 2) == 0 ? tM : tD;
-                    } else if (s0 == tI) {
-                        const int q = (k - 1) % Q, r = (k - 1) / Q;
-                        const float *pr = dp + (size_t)(i - 1) * RW + (size_t)q * 12 + r;
-                        path[0] = md_mul(pr[0], tfv[(size_t)q * 28 + 20 + r]);
-                        path[1] = md_mul(pr[8], tfv[(size_t)q * 28 + 24 + r]);
-                        s1 = md_choose(rng, path, 2) == 0 ? tM : tI;
-                        i--;
-                    } else if (s0 == tN) {
-                        s1 = (i == 0) ? tS : tN;
-                    } else if (s0 == tC) {
-                        path[0] = md_mul(ploop, x0[4]);
-                        path[1] = md_mul(md_mul(0.5f, x1[0]), x1[5]);
-                        s1 = md_choose(rng, path, 2) == 0 ? tC : tE;
-                    } else if (s0 == tJ) {
-                        path[0] = md_mul(ploop, x0[2]);
-                        path[1] = md_mul(md_mul(0.5f, x1[0]), x1[5]);
-                        s1 = md_choose(rng, path, 2) == 0 ? tJ : tE;
-                    } else {   // B
-                        path[0] = md_mul(pmove, x1[1]);
-                        path[1] = md_mul(pmove, x1[2]);
-                        s1 = md_choose(rng, path, 2) == 0 ? tN : tJ;
+                        for (int o = 16; o > 0; o >>= 1) sx += __shfl_xor_sync(FULL, sx, o);
+                        if (lane == 0) s_null2[w][x] = (float)(sx * (double)nrm);
                     }
                 }
-                if (s0 != tE) { s1 = __shfl_sync(FULL, s1, 0); i = __shfl_sync(FULL, i, 0); k = __shfl_sync(FULL, k, 0); }
-                // bookkeeping of the running domain (every lane keeps the same copy; the emission sums on lane 0)
-                if (s1 == tM || s1 == tI) {
-                    if (s1 == tM) { if (sqto == 0) { sqto = i; hto = k; } sqfrom = i; hfrom = k; }
-                    Ld++;
-                    if (lane == 0) {   // 3.1b2 counts a residue emitted by I_k in the MATCH cell of node k
-                        const int q = (k - 1) % Q, r = (k - 1) / Q;
-                        for (int x = 0; x < K; x++) sums[x] += (double)rfv[((size_t)x * Q + q) * 4 + r];
+                __syncwarp();
+                for (int p = sqto + 1 + lane; p <= hi; p += 32) acc[p] = md_add(acc[p], 1.0f);
+                for (int p = sqfrom + 1 + lane; p <= sqto; p += 32) {
+                    const int code = Qs.symrow[rd[p - 1]];
+                    float v;
+                    if (code < K) v = s_null2[w][code];
+                    else {
+                        const unsigned mask = md_degen_mask(E.Kp, code);
+                        float sg = 0.f; int n = 0;
+                        for (int x = 0; x < K; x++) if (mask >> x & 1u) { sg += s_null2[w][x]; n++; }
+                        v = n ? sg / (float)n : 1.0f;
                     }
-                } else if (s1 == tB) {
-                    // domain sqfrom..sqto complete: null2 odds of the trace's domain, accumulated per residue
-                    if (lane == 0) {
-                        const float nrm = (float)(1.0 / (double)(float)Ld);
-                        for (int x = 0; x < K; x++) s_null2[w][x] = (float)(sums[x] * (double)nrm);
-                    }
-                    __syncwarp();
-                    for (int p = sqto + 1 + lane; p <= hi; p += 32) acc[p] = md_add(acc[p], 1.0f);
-                    for (int p = sqfrom + 1 + lane; p <= sqto; p += 32) {
-                        const int code = Qs.symrow[rd[p - 1]];
-                        float v;
-                        if (code < K) v = s_null2[w][code];
-                        else {
-                            const unsigned mask = md_degen_mask(E.Kp, code);
-                            float s = 0.f; int n = 0;
-                            for (int x = 0; x < K; x++) if (mask >> x & 1u) { s += s_null2[w][x]; n++; }
-                            v = n ? s / (float)n : 1.0f;
-                        }
-                        acc[p] = md_add(acc[p], v);
-                    }
-                    hi = sqfrom;   // (HMMER gives residue sqfrom the neutral 1.0 as well)
-                    if (ndom < MD_MAXDOM && lane == 0) { s_dom[w][ndom][0] = sqfrom; s_dom[w][ndom][1] = sqto; s_dom[w][ndom][2] = hfrom; s_dom[w][ndom][3] = hto; }
-                    ndom++;
-                    __syncwarp();
+                    acc[p] = md_add(acc[p], v);
                 }
-                if ((s1 == tN || s1 == tJ || s1 == tC) && s1 == s0) i--;
-                s0 = s1;
+                hi = sqfrom;   // (HMMER gives residue sqfrom the neutral 1.0 as well)
+                if (ndom < MD_MAXDOM && lane == 0) { s_dom[w][ndom][0] = sqfrom; s_dom[w][ndom][1] = sqto; s_dom[w][ndom][2] = hfrom; s_dom[w][ndom][3] = hto; }
+                ndom++;
+                sqto = 0; sqfrom = 0; hto = 0; hfrom = 0; Ld = 0;
+                __syncwarp();
             }
             for (int p = 1 + lane; p <= hi; p += 32) acc[p] = md_add(acc[p], 1.0f);
             // the trace's domains enter the ensemble in sequence order (they were found last to first)
@@ -396,6 +479,7 @@ __global__ void __launch_bounds__(MD_WARPS * 32) md_region_kernel(DevEhmm E, Dev
         for (int o = 16; o > 0; o >>= 1) regc += __shfl_xor_sync(FULL, regc, o);
         __syncwarp();
 
+        const long long clk2 = clock64();
         // ====================== single-linkage clustering of the sampled domains ======================
         for (int a = lane; a < nsp; a += 32) asg[a] = a;
         __syncwarp();
@@ -497,6 +581,7 @@ __global__ void __launch_bounds__(MD_WARPS * 32) md_region_kernel(DevEhmm E, Dev
                 } else fl = 4;
             }
             out->nclust = nout; out->flags = fl; out->regcorr = regc;
+            out->clk[0] = clk1 - clk0; out->clk[1] = clk2 - clk1; out->clk[2] = clock64() - clk2; out->clk[3] = ((long long)Lr << 32) | (unsigned)M;
         }
         __syncwarp();
     }

@@ -58,14 +58,15 @@ constexpr int W_SCALE_EVERY = 8;
 #define WITCH_WAVE_UNROLL_B 2
 #endif
 constexpr int W_UNROLL_F = WITCH_WAVE_UNROLL_F, W_UNROLL_B = WITCH_WAVE_UNROLL_B;
-// Prepared experiments (bit mask, default 0 = the measured round-1 kernel):
+// Issue-slot trims of the Backward step (bit mask; 7 = all three is the default since round 2: +5 % on the envelope pass,
+// bit-identical scores; 0 = the round-1 kernel):
 //   1: the lane that issues a TMA copy is chosen with elect.sync instead of `lane == 0` (all operands are warp-uniform);
 //      ptxas then drops the ELECT/R2UR "waterfall" loop it builds around UBLKCP for a possibly divergent issuer
 //   2: the once-per-8-steps exponent-block switch of the Backward step is a real (warp-uniform) branch instead of 16
 //      predicated-off instructions in every step
 //   4: steady-state Backward steps skip the "rows left to request?" test of the Forward-row ring (always true there)
 #ifndef WITCH_WAVE_EXP
-#define WITCH_WAVE_EXP 0
+#define WITCH_WAVE_EXP 7
 #endif
 constexpr int W_EXP = WITCH_WAVE_EXP;
 // Stored Forward match rows of the ENVELOPE pass (DNA/RNA, warp-uniform exponent) in 16 bits: halves the pass's HBM traffic
