@@ -246,30 +246,74 @@ extern "C" int witch_score_dev(witch_ehmm *e, witch_queries *q, float *d_scores,
         HostClock hc;
         run_parser(e, q, qs, hs, nullptr, st);
         hc.lap("parser");
-        // ---- region counts, scans, totals: the only host-visible numbers are the sizes of the two lists ----
+        // ---- region counts, scans, totals: the host learns the sizes of the two lists and the bucket shapes of the first ----
         const unsigned nb = (unsigned)((np + 255) / 256);
-        e->cntA.alloc(np); e->cntB.alloc(np); e->baseA.alloc(np); e->baseB.alloc(np); e->desc.alloc(1);
+        e->cntA.alloc(np); e->cntB.alloc(np); e->baseA.alloc(np); e->baseB.alloc(np); e->desc.alloc(2);
         e->counter.alloc(64);
         CUDA_TRY(cudaMemsetAsync(e->counter.p, 0, 64 * sizeof(unsigned), st));
-        CUDA_TRY(cudaMemsetAsync(e->desc.p, 0, sizeof(WlDesc), st));
-        WITCH_LAUNCH(region_count_kernel, nb, 256, 0, st)(e->parse.p, np, e->cntA.p, e->cntB.p);
+        CUDA_TRY(cudaMemsetAsync(e->desc.p, 0, 2 * sizeof(WlDesc), st));
+        WITCH_LAUNCH(region_count_kernel, nb, 256, 0, st)(e->parse.p, np, H, e->dM.p, e->cntA.p, e->cntB.p, e->desc.p);
         dev_exclusive_sum(e, e->cntA.p, e->baseA.p, np, st);
         dev_exclusive_sum(e, e->cntB.p, e->baseB.p, np, st);
         WITCH_LAUNCH(scan_totals_kernel, 1, 32, 0, st)(e->cntA.p, e->baseA.p, e->cntB.p, e->baseB.p, np, e->desc.p);
         g_launches += 2;
         CUDA_TRY(cudaMemcpyAsync(e->hdesc, e->desc.p, sizeof(WlDesc), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));   // sizing step 1: how many single-domain / multi-domain regions
+        CUDA_TRY(cudaStreamSynchronize(st));   // sizing step 1
         const int nA = e->hdesc->totals[0], nmd = e->hdesc->totals[1];
-        const long long NI = (long long)nA + (long long)nmd * MD_MAXC;
+        const long long NB = (long long)nmd * MD_MAXC, NI = (long long)nA + NB, NL = std::max<long long>(nA, NB);
         hc.lap("region lists");
         e->f1.alloc((size_t)NI + 1); e->f2.alloc((size_t)NI + 1);
-        e->items.alloc((size_t)NI + 1); e->items2.alloc((size_t)NI + 1); e->keys.alloc((size_t)NI + 1); e->keys2.alloc((size_t)NI + 1);
+        e->items.alloc((size_t)NL + 1); e->items2.alloc((size_t)NL + 1); e->keys.alloc((size_t)NL + 1); e->keys2.alloc((size_t)NL + 1);
+        e->runhead.alloc((size_t)NL + 1); e->runstart.alloc((size_t)NL + 1); e->gflag.alloc((size_t)NL + 1); e->gid.alloc((size_t)NL + 1);
+        e->group_first.alloc((size_t)NL + 1); e->grange.alloc(64);
         e->mdregs.alloc((size_t)nmd + 1); e->mdout.alloc((size_t)nmd + 1);
+        int maxM_small = 0, maxM_big = 0;
+        for (int h = 0; h < H; h++) { if (e->M[h] > 13 * 256) maxM_big = std::max(maxM_big, e->M[h]); else maxM_small = std::max(maxM_small, e->M[h]); }
+        // sorts the n items in e->items/e->keys, cuts groups, returns the launches described by `hd` (counters from cbase)
+        auto build_and_launch = [&](long long n, const WlDesc *hd, int cbase, int *grange) {
+            dev_sort_items(e, e->keys.p, e->keys2.p, e->items.p, e->items2.p, n, st);
+            const unsigned nbi = (unsigned)((n + 255) / 256);
+            CUDA_TRY(cudaMemsetAsync(grange, 0, 32 * sizeof(int), st));
+            WITCH_LAUNCH(group_head_kernel, nbi, 256, 0, st)(e->keys2.p, (int)n, e->runhead.p);
+            dev_inclusive_max(e, e->runhead.p, e->runstart.p, n, st);
+            WITCH_LAUNCH(group_flag_kernel, nbi, 256, 0, st)(e->keys2.p, e->runstart.p, (int)n, WITCH_ENV_WARPS, e->gflag.p);
+            dev_exclusive_sum(e, e->gflag.p, e->gid.p, n, st);
+            WITCH_LAUNCH(group_scatter_kernel, nbi, 256, 0, st)(e->keys2.p, e->gflag.p, e->gid.p, (int)n, e->group_first.p, grange);
+            g_launches += 3;
+            std::vector<WaveLaunch> launches;
+            long long off = 0;
+            for (int b = 0; b < WL_BUCKETS; b++) {
+                const int cnt = hd->count[b];
+                if (cnt == 0) continue;
+                WaveLaunch L;
+                off += cnt;
+                L.item_end = (int)off; L.nitems = cnt; L.Lcap = hd->maxLs[b]; L.maxM = (b & 1) ? maxM_big : maxM_small;
+                L.cells = hd->cells[b]; L.grange = grange + 2 * b; L.counter = e->counter.p + cbase + b;
+                launches.push_back(L);
+            }
+            run_wave<false>(e, q, e->items2.p, e->group_first.p, launches, e->f1.p, e->f2.p, nullptr, nullptr, nullptr, nullptr, st);
+        };
+        // ---- the multi-domain branch runs on the handle's side stream, next to the envelope pass of everything else ----
         if (nmd > 0) {
+            e->ensure_aux();
             WITCH_LAUNCH(md_list_kernel, nb, 256, 0, st)(e->parse.p, np, H, e->baseB.p, e->mdregs.p);
             g_launches++;
-            run_md(e, q, nmd, st);
-            hc.lap("multi-domain branch");
+            CUDA_TRY(cudaEventRecord(e->ev_fork, st));
+            CUDA_TRY(cudaStreamWaitEvent(e->aux, e->ev_fork, 0));
+            run_md(e, q, nmd, e->aux);
+            CUDA_TRY(cudaEventRecord(e->ev_join, e->aux));
+        }
+        if (nA > 0) {
+            WITCH_LAUNCH(items_sd_kernel, nb, 256, 0, st)(e->parse.p, np, H, e->baseA.p, e->dhrank.p, e->dM.p, e->items.p, e->keys.p);
+            g_launches++;
+            const WlDesc hd1 = *e->hdesc;
+            build_and_launch(nA, &hd1, 0, e->grange.p);
+            hc.lap("envelope pass (single-domain regions) + multi-domain branch");
+        }
+        if (nmd > 0) {
+            CUDA_TRY(cudaStreamWaitEvent(st, e->ev_join, 0));
+            // (the first list's buffers are reused: its launches are complete once the host has the second descriptor)
+            CUDA_TRY(cudaStreamSynchronize(st));
             if (hc.on) {   // WITCH_TIMING: where the branch spends its time (device clock ticks per region)
                 std::vector<MdOut> mo(nmd);
                 CUDA_TRY(cudaMemcpy(mo.data(), e->mdout.p, (size_t)nmd * sizeof(MdOut), cudaMemcpyDeviceToHost));
@@ -284,44 +328,14 @@ extern "C" int witch_score_dev(witch_ehmm *e, witch_queries *q, float *d_scores,
                         nmd, s0 / nmd / 1e6, s1 / nmd / 1e6, s2 / nmd / 1e6, m0 / 1e6, m1 / 1e6, m2 / 1e6, (int)(mo[wi].clk[3] >> 32), (int)(mo[wi].clk[3] & 0xffffffff),
                         mo[wi].clk[0] / 1e6, mo[wi].clk[1] / 1e6, mo[wi].clk[2] / 1e6);
             }
-        }
-        if (NI > 0) {
-            WITCH_LAUNCH(items_sd_kernel, nb, 256, 0, st)(e->parse.p, np, H, e->baseA.p, e->dhrank.p, e->dM.p, e->items.p, e->keys.p, e->desc.p);
+            WITCH_LAUNCH(items_md_kernel, (unsigned)((NB + 255) / 256), 256, 0, st)(e->mdregs.p, e->mdout.p, nmd, nA, e->dhrank.p, e->dM.p,
+                                                                                e->items.p, e->keys.p, e->desc.p + 1);
             g_launches++;
-            if (nmd > 0) {
-                WITCH_LAUNCH(items_md_kernel, (unsigned)((nmd * MD_MAXC + 255) / 256), 256, 0, st)(e->mdregs.p, e->mdout.p, nmd, nA, e->dhrank.p,
-                                                                                            e->dM.p, e->items.p, e->keys.p, e->desc.p);
-                g_launches++;
-            }
-            dev_sort_items(e, e->keys.p, e->keys2.p, e->items.p, e->items2.p, NI, st);
-            e->runhead.alloc((size_t)NI); e->runstart.alloc((size_t)NI); e->gflag.alloc((size_t)NI); e->gid.alloc((size_t)NI);
-            e->group_first.alloc((size_t)NI + 1); e->grange.alloc(32);
-            const unsigned nbi = (unsigned)((NI + 255) / 256);
-            CUDA_TRY(cudaMemsetAsync(e->grange.p, 0, 32 * sizeof(int), st));
-            WITCH_LAUNCH(group_head_kernel, nbi, 256, 0, st)(e->keys2.p, (int)NI, e->runhead.p);
-            dev_inclusive_max(e, e->runhead.p, e->runstart.p, NI, st);
-            WITCH_LAUNCH(group_flag_kernel, nbi, 256, 0, st)(e->keys2.p, e->runstart.p, (int)NI, WITCH_ENV_WARPS, e->gflag.p);
-            dev_exclusive_sum(e, e->gflag.p, e->gid.p, NI, st);
-            WITCH_LAUNCH(group_scatter_kernel, nbi, 256, 0, st)(e->keys2.p, e->gflag.p, e->gid.p, (int)NI, e->group_first.p, e->grange.p);
-            g_launches += 3;
-            CUDA_TRY(cudaMemcpyAsync(e->hdesc, e->desc.p, sizeof(WlDesc), cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaStreamSynchronize(st));   // sizing step 2: items / longest envelope of every bucket
-            hc.lap("work list (device)");
-            std::vector<WaveLaunch> launches;
-            int maxM_small = 0, maxM_big = 0;
-            for (int h = 0; h < H; h++) { if (e->M[h] > 13 * 256) maxM_big = std::max(maxM_big, e->M[h]); else maxM_small = std::max(maxM_small, e->M[h]); }
-            long long off = 0;
-            for (int b = 0; b < WL_BUCKETS; b++) {
-                const int cnt = e->hdesc->count[b];
-                if (cnt == 0) continue;
-                WaveLaunch L;
-                off += cnt;
-                L.item_end = (int)off; L.nitems = cnt; L.Lcap = e->hdesc->maxLs[b]; L.maxM = (b & 1) ? maxM_big : maxM_small;
-                L.cells = e->hdesc->cells[b]; L.grange = e->grange.p + 2 * b; L.counter = e->counter.p + b;
-                launches.push_back(L);
-            }
-            run_wave<false>(e, q, e->items2.p, e->group_first.p, launches, e->f1.p, e->f2.p, nullptr, nullptr, nullptr, nullptr, st);
-            hc.lap("run_wave (all buckets)");
+            CUDA_TRY(cudaMemcpyAsync(e->hdesc, e->desc.p + 1, sizeof(WlDesc), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));   // sizing step 2 (only when some region took the multi-domain branch)
+            const WlDesc hd2 = *e->hdesc;
+            build_and_launch(NB, &hd2, 16, e->grange.p + 32);
+            hc.lap("envelope pass (multi-domain envelopes)");
         }
         WITCH_LAUNCH(finalize_scores_kernel, (unsigned)((np + 255) / 256), 256, 0, st)(e->parse.p, q->dlen.p, nq, H, e->baseA.p, e->baseB.p,
                                                                            e->mdout.p, nA, e->f1.p, e->f2.p, d_scores, d_reported,

@@ -303,6 +303,7 @@ __global__ void __launch_bounds__(MD_WARPS * 32) md_region_kernel(DevEhmm E, Dev
             // model nodes are listed in tkb[].
             int i = Lr, k = 0, s0 = tC, ndom = 0, hi = Lr;
             int sqto = 0, sqfrom = 0, hto = 0, hfrom = 0, Ld = 0;
+            int cq = 0, cr = 0;   // (k-1) % Q and (k-1) / Q of the current node, kept incrementally (no divisions per step)
             for (;;) {
                 int ev = 0;
                 if (lane == 0) {
@@ -314,7 +315,8 @@ __global__ void __launch_bounds__(MD_WARPS * 32) md_region_kernel(DevEhmm E, Dev
                         float path[4];
                         if (s0 == tM) {
                             k--;
-                            const int q = k % Q, r = k / Q;
+                            const int q = cq, r = cr;   // = k % Q, k / Q of the decremented k
+                            if (--cq < 0) { cq += Q; cr--; }
                             const float *tp = tfv + (size_t)q * 28 + r;
                             const float *pr = dp + (size_t)(i - 1) * RW;
                             float mp = 0.f, dd = 0.f, ip = 0.f;
@@ -339,20 +341,21 @@ __global__ void __launch_bounds__(MD_WARPS * 32) md_region_kernel(DevEhmm E, Dev
                             i--;
                         } else if (s0 == tD) {
                             k--;
-                            const int q = k % Q, r = k / Q;
-                            const float *cr = dp + (size_t)i * RW;
+                            const int q = cq, r = cr;
+                            if (--cq < 0) { cq += Q; cr--; }
+                            const float *crow = dp + (size_t)i * RW;
                             float mp = 0.f, dd = 0.f, tmd = 0.f, tdd = 0.f;
                             if (q > 0) {
-                                mp = cr[(size_t)(q - 1) * 12 + r]; dd = cr[(size_t)(q - 1) * 12 + 4 + r];
+                                mp = crow[(size_t)(q - 1) * 12 + r]; dd = crow[(size_t)(q - 1) * 12 + 4 + r];
                                 tmd = tfv[(size_t)(q - 1) * 28 + 16 + r]; tdd = tfv[(size_t)Q * 28 + (size_t)(q - 1) * 4 + r];
                             } else if (r > 0) {
-                                mp = cr[(size_t)(Q - 1) * 12 + r - 1]; dd = cr[(size_t)(Q - 1) * 12 + 4 + r - 1];
+                                mp = crow[(size_t)(Q - 1) * 12 + r - 1]; dd = crow[(size_t)(Q - 1) * 12 + 4 + r - 1];
                                 tmd = tfv[(size_t)(Q - 1) * 28 + 16 + r - 1]; tdd = tfv[(size_t)Q * 28 + (size_t)(Q - 1) * 4 + r - 1];
                             }
                             path[0] = md_mul(mp, tmd); path[1] = md_mul(dd, tdd);
                             s1 = md_choose(rng, path, 2) == 0 ? tM : tD;
                         } else if (s0 == tI) {
-                            const int q = (k - 1) % Q, r = (k - 1) / Q;
+                            const int q = cq, r = cr;
                             const float *pr = dp + (size_t)(i - 1) * RW + (size_t)q * 12 + r;
                             path[0] = md_mul(pr[0], tfv[(size_t)q * 28 + 20 + r]);
                             path[1] = md_mul(pr[8], tfv[(size_t)q * 28 + 24 + r]);
@@ -418,6 +421,7 @@ __global__ void __launch_bounds__(MD_WARPS * 32) md_region_kernel(DevEhmm E, Dev
                     }
                     // a new domain starts (seen from its end)
                     k = kk; s0 = ss;
+                    cq = (kk - 1) % Q; cr = (kk - 1) / Q;
                     sqto = 0; sqfrom = 0; hto = 0; hfrom = 0; Ld = 0;
                     if (ss == tM) { sqto = i; hto = kk; sqfrom = i; hfrom = kk; if (lane == 0) tkb[0] = kk; Ld = 1; }
                     continue;

@@ -118,7 +118,19 @@ struct witch_ehmm {
     DevBuf<WlDesc> desc;
     DevBuf<long long> coloff;
     WlDesc *hdesc = nullptr;   // pinned host copy of the work-list descriptor
-    ~witch_ehmm() { if (hdesc) cudaFreeHost(hdesc); }
+    // side stream for the multi-domain branch (runs next to the envelope pass of the single-domain regions)
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    void ensure_aux() {
+        if (aux) return;
+        CUDA_TRY(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    }
+    ~witch_ehmm() {
+        if (hdesc) cudaFreeHost(hdesc);
+        if (aux) { cudaStreamDestroy(aux); cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join); }
+    }
     DevEhmm view() const {
         DevEhmm v;
         v.tMM = tMM.p; v.tMI = tMI.p; v.tMD = tMD.p; v.tIM = tIM.p; v.tII = tII.p; v.tDM = tDM.p; v.tDD = tDD.p;

@@ -27,14 +27,24 @@ struct WlDesc {   // filled by atomics on the device, read once by the host to s
     int totals[4];   // [0] single-domain regions (A slots), [1] multi-domain regions
 };
 
-// per pair: number of single-domain regions (cntA) and multi-domain regions (cntB)
-__global__ void region_count_kernel(const PairParse *parse, long long np, int *cntA, int *cntB) {
+// per pair: number of single-domain regions (cntA) and multi-domain regions (cntB); the single-domain regions are the
+// envelope items of the first work list, so their bucket descriptor is accumulated here as well
+__global__ void region_count_kernel(const PairParse *parse, long long np, int H, const int *M, int *cntA, int *cntB, WlDesc *desc) {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= np) return;
-    const int n = parse[p].nenv, md = (parse[p].flags >> 8) & ((1 << n) - 1);
+    const PairParse pp = parse[p];
+    const int n = pp.nenv, md = (pp.flags >> 8) & ((1 << n) - 1);
     const int nb = __popc((unsigned)md);
     cntA[p] = n - nb;
     cntB[p] = nb;
+    const int Mh = M[(int)(p % H)];
+    for (int r = 0; r < n; r++)
+        if (!(md >> r & 1)) {
+            const int Ls = pp.env_j[r] - pp.env_i[r] + 1, b = wl_bucket(Ls, Mh);
+            atomicAdd(&desc->count[b], 1);
+            atomicMax(&desc->maxLs[b], Ls);
+            atomicAdd(&desc->cells[b], (double)Ls * (double)Mh);
+        }
 }
 
 // totals of the two scans (last base + last count)
@@ -63,36 +73,39 @@ __device__ __forceinline__ void wl_emit(WaveItem *items, unsigned long long *key
     items[slot] = it;
     const int b = wl_bucket(Ls, M[h]);
     keys[slot] = wl_key(b, hrank[h], Ls);
-    atomicAdd(&desc->count[b], 1);
-    atomicMax(&desc->maxLs[b], Ls);
-    atomicAdd(&desc->cells[b], (double)Ls * (double)M[h]);
+    if (desc) {
+        atomicAdd(&desc->count[b], 1);
+        atomicMax(&desc->maxLs[b], Ls);
+        atomicAdd(&desc->cells[b], (double)Ls * (double)M[h]);
+    }
 }
 
-// single-domain regions -> items [0, nA)
+// single-domain regions -> items [0, nA) (output slot = item index)
 __global__ void items_sd_kernel(const PairParse *parse, long long np, int H, const int *baseA, const int *hrank, const int *M,
-                                WaveItem *items, unsigned long long *keys, WlDesc *desc) {
+                                WaveItem *items, unsigned long long *keys) {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= np) return;
     const PairParse pp = parse[p];
     int slot = baseA[p];
     for (int r = 0; r < pp.nenv; r++)
         if (!(pp.flags >> (8 + r) & 1))
-            wl_emit(items, keys, desc, slot++, (int)(p / H), (int)(p % H), pp.env_i[r], pp.env_j[r] - pp.env_i[r] + 1, hrank, M);
+            wl_emit(items, keys, nullptr, slot++, (int)(p / H), (int)(p % H), pp.env_i[r], pp.env_j[r] - pp.env_i[r] + 1, hrank, M);
 }
 
-// envelopes of the multi-domain regions -> items [nA + m*MD_MAXC, ...): unused slots get a sentinel key
+// envelopes of the multi-domain regions -> the second work list, items [0, nmd*MD_MAXC) with output slots nA + index;
+// unused entries get a sentinel key
 __global__ void items_md_kernel(const MdRegion *regs, const MdOut *mdout, int nmd, int nA, const int *hrank, const int *M,
                                 WaveItem *items, unsigned long long *keys, WlDesc *desc) {
     const int z = blockIdx.x * blockDim.x + threadIdx.x;
     if (z >= nmd * MD_MAXC) return;
     const int m = z / MD_MAXC, c = z - m * MD_MAXC;
-    const int slot = nA + z;
     if (c < mdout[m].nclust) {
-        wl_emit(items, keys, desc, slot, regs[m].q, regs[m].h, mdout[m].ci[c], mdout[m].cj[c] - mdout[m].ci[c] + 1, hrank, M);
+        wl_emit(items, keys, desc, z, regs[m].q, regs[m].h, mdout[m].ci[c], mdout[m].cj[c] - mdout[m].ci[c] + 1, hrank, M);
+        items[z].pair = nA + z;
     } else {
-        WaveItem it; it.q = 0; it.h = 0; it.i0 = 1; it.Ls = 0; it.pair = slot;
-        items[slot] = it;
-        keys[slot] = wl_key(WL_SENTINEL_BUCKET, 0, 0);
+        WaveItem it; it.q = 0; it.h = 0; it.i0 = 1; it.Ls = 0; it.pair = nA + z;
+        items[z] = it;
+        keys[z] = wl_key(WL_SENTINEL_BUCKET, 0, 0);
     }
 }
 
