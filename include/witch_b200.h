@@ -29,9 +29,11 @@ extern "C" {
 #define WITCH_ALPH_AMINO 2
 
 /* flag bits of witch_score's per-pair flags */
-#define WITCH_FLAG_MULTIDOMAIN 1 /* a region failed HMMER's single-domain test (rt3); kept as one envelope */
+#define WITCH_FLAG_MULTIDOMAIN 1 /* a region failed HMMER's single-domain test and was resolved the way hmmsearch does:
+                                    200 stochastic tracebacks over the region + clustering into envelopes (informational) */
 #define WITCH_FLAG_SUMSCORE 2    /* the reconstruction ("sum") score overrode the per-sequence score */
-#define WITCH_FLAG_ENVCAP 4      /* more than 6 envelopes were found for the pair; the first 6 were scored */
+#define WITCH_FLAG_ENVCAP 4      /* a built-in cap was hit (> 6 regions for the pair, or > 16 envelopes / > 4096 sampled
+                                    domains in one multi-domain region); what fits was scored */
 
 typedef struct witch_ehmm witch_ehmm;       /* an ensemble of profile HMMs resident on one GPU */
 typedef struct witch_queries witch_queries; /* a digitised, packed query set resident on one GPU */
@@ -82,7 +84,14 @@ int witch_score(witch_ehmm *e, witch_queries *q, float *scores, uint8_t *reporte
 /*
  * Same, results left on the device: d_scores/d_reported/(d_pre, d_flags may be NULL) are DEVICE pointers to
  * [n_queries][n_hmm] arrays (e.g. torch tensors' data_ptr()). Work is enqueued on `stream` (a cudaStream_t
- * passed as void*; NULL = default stream) and the call returns without synchronising.
+ * passed as void*; NULL = default stream). The envelope work list is built on the device; the call synchronises
+ * `stream` ONCE to learn its size (a 400-byte read-back after the parser pass) -- and a second and third time only
+ * if some region took the multi-domain branch (that branch runs on a side stream of the handle, next to the
+ * envelope pass of all other regions; the stream then waits for it). Scratch buffers belong to the handle and are
+ * reused between calls: once they have grown to the workload's size a call neither allocates nor frees.
+ * The final kernels are left running on `stream` when the call returns.
+ * Limits are checked before anything is enqueued (WITCH_ERR_LIMIT): models <= 8192 nodes, and
+ * (distinct query symbols) x (model nodes) <= ~50,000 (8192 nodes for plain DNA/RNA, ~2,000 for protein).
  */
 int witch_score_dev(witch_ehmm *e, witch_queries *q, float *d_scores, uint8_t *d_reported, float *d_pre,
                     uint8_t *d_flags, void *stream);
@@ -109,8 +118,9 @@ int witch_weights_topk_dev(const witch_ehmm *e, const float *d_scores, const uin
  */
 int witch_align(witch_ehmm *e, witch_queries *q, int n_pairs, const int32_t *qidx, const int32_t *hidx,
                 const int64_t *col_offsets, int32_t *cols);
-/* Device-pointer variant: d_qidx, d_hidx, d_col_offsets, d_cols are device memory; asynchronous on `stream`
- * except for one internal sizing step. */
+/* Device-output variant: h_qidx, h_hidx, h_col_offsets are HOST arrays (the pair list comes from the caller's
+ * host-side inclusion logic), d_cols is device memory. Everything is enqueued on `stream`; the call does not
+ * synchronise (except while the handle's scratch buffers are still growing). */
 int witch_align_dev(witch_ehmm *e, witch_queries *q, int n_pairs, const int32_t *h_qidx, const int32_t *h_hidx,
                     const int64_t *h_col_offsets, int32_t *d_cols, void *stream);
 
@@ -156,8 +166,10 @@ int witch_merge_rows(witch_ehmm *e, int nrows, const int64_t *row_off, const int
 uint64_t witch_kernel_launches(void);
 void witch_prof_enable(int on);
 void witch_prof_reset(void);
-/* which: 0 = multihit Forward/Backward parser kernel, 1 = envelope (unihit) kernels, 2 = align kernels.
- * Returns accumulated ms and (via *cells) the DP cells those launches covered. */
+/* which: 0 = multihit Forward/Backward parser kernel, 1 = envelope (unihit) kernels, 2 = align kernels,
+ * 3 = multi-domain branch (runs concurrently with 1; cells not counted).
+ * Returns accumulated ms and (via *cells) the DP cells those launches covered. Timed launches leave CUDA events
+ * behind that are resolved here (this call synchronises on them; the stage calls do not). */
 double witch_prof_get(int which, double *cells, uint64_t *launches);
 
 /* Measured FP32 FMA throughput of the current device in TFLOP/s (2 flop per FMA lane-op): a dependent-chain-free

@@ -173,11 +173,15 @@ def test_mirror_interface_end_to_end(wb, tmp_path):
     """BatchedSearch mirrors the reference's function contracts (types and content)."""
     from witch_b200.gcmm import BatchedSearch
     gold, queries, paths = load_set("dna_small", str(tmp_path))
-    bs = BatchedSearch(paths, num_hmms=10)
+    rt = str(tmp_path / "runtime_breakdown.txt")
+    bs = BatchedSearch(paths, num_hmms=10, runtime_path=rt)
     bs.search([n for n, _ in queries], [s for _, s in queries])
     ranked = bs.rankBitscores()
     t2w = bs.writeWeights()
     bb = bs.getBackbones(t2w)
+    lines = open(rt).read().splitlines()   # the reference's runtime_breakdown.txt format: "(tag) Time to ... (s): x"
+    assert [ln.split(")")[0] for ln in lines] == ["(gpu_score", "(gpu_weights", "(gpu_align"]
+    assert all(" (s): " in ln and float(ln.rsplit(": ", 1)[1]) >= 0 for ln in lines)
     names = [n for n, _ in queries]
     for h, hg in enumerate(gold["hmms"]):
         res = bs.hmmsearch_results(h)

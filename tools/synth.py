@@ -211,7 +211,7 @@ def _run_hmmbuild(job):
     return _hmmbuild_leng(hmm_path) == ncols
 
 
-def make_workload(outdir, alphabet="dna", n_total=10000, n_backbone=1000, root_len=1550, decomp=10, frag_frac=0.25,
+def make_workload(outdir, alphabet="dna", c1=False, n_total=10000, n_backbone=1000, root_len=1550, decomp=10, frag_frac=0.25,
                   frag_mean=400, seed=1, n_queries=None, max_hmms=None, mean_blen=0.02, indel_rate=0.0065,
                   profiles="auto"):
     """Build (or reuse) a workload directory. Returns dict(hmm_paths, nseq, names, seqs, retained_columns,
@@ -219,6 +219,8 @@ def make_workload(outdir, alphabet="dna", n_total=10000, n_backbone=1000, root_l
     built-in estimator) or "auto" (hmmbuild when oracle/_ref is staged)."""
     if profiles == "auto":
         profiles = "hmmbuild" if os.access(HMMBUILD, os.X_OK) else "pseudocount"
+    if c1:
+        return make_workload_c1(outdir, max_hmms=max_hmms)
     key = hashlib.sha1(repr((alphabet, n_total, n_backbone, root_len, decomp, frag_frac, frag_mean, seed, n_queries,
                              max_hmms, mean_blen, indel_rate, "v6", profiles)).encode()).hexdigest()[:12]
     wd = os.path.join(outdir, "synth_" + key)
@@ -296,8 +298,72 @@ def make_workload(outdir, alphabet="dna", n_total=10000, n_backbone=1000, root_l
                 nongaps_per_column=nongaps, backbone_length=backbone_length, meta=meta)
 
 
+def make_workload_c1(outdir, max_hmms=None, decomp=10, **_):
+    """BASELINE config c1: the reference's bundled nucleotide example (examples/data: 500-sequence backbone alignment,
+    500 fragments), from the copies committed under tests/golden/c1 by tests/golden/make_golden_c1.py. The eHMM is the
+    hierarchical decomposition WITCH builds with `-A 10` (every subtree above 10 leaves plus the leaves' subtrees:
+    1 + 2 + ... + 64 = 127 subsets); the tree itself is not on the hot path, so the backbone rows are halved in file order
+    (subset SIZES match the reference's). Profiles: the reference's hmmbuild with WITCH's flags (oracle/_ref)."""
+    import gzip
+    gdir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "c1")
+
+    def rd(path):
+        out = []
+        with gzip.open(path, "rt") as f:
+            for ln in f:
+                ln = ln.strip()
+                if ln.startswith(">"):
+                    out.append([ln[1:].split()[0], ""])
+                elif ln:
+                    out[-1][1] += ln
+        return out
+    bb = rd(os.path.join(gdir, "backbone.fasta.gz"))
+    qs = rd(os.path.join(gdir, "queries_all.fasta.gz"))
+    if not os.access(HMMBUILD, os.X_OK):
+        raise RuntimeError("config c1 needs the staged reference hmmbuild (oracle/_ref/hmmer/hmmbuild)")
+    lut = {c: i for i, c in enumerate(DNA)}
+    rows = np.full((len(bb), len(bb[0][1])), -1, dtype=np.int8)
+    for r, (_, s) in enumerate(bb):
+        a = np.frombuffer(s.upper().encode(), dtype=np.uint8)
+        for c, i in lut.items():
+            rows[r, a == ord(c)] = i
+        rows[r, (a != ord("-")) & (rows[r] < 0)] = 0   # (degenerate backbone letters, if any, count as residues)
+    subsets = []
+
+    def split(lo, hi):
+        subsets.append((lo, hi))
+        if hi - lo > decomp:
+            mid = (lo + hi) // 2
+            split(lo, mid); split(mid, hi)
+    split(0, len(bb))
+    subsets.sort(key=lambda x: (-(x[1] - x[0]), x[0]))   # breadth-first order like the reference's labels
+    if max_hmms:
+        subsets = subsets[:max_hmms]
+    wd = os.path.join(outdir, "c1_%d_%s" % (decomp, max_hmms))
+    os.makedirs(wd, exist_ok=True)
+    hmm_paths, nseqs, retained, nongaps, jobs = [], [], [], [], []
+    for si, (lo, hi) in enumerate(subsets):
+        sub = rows[lo:hi]
+        cols = np.nonzero((sub >= 0).any(0))[0]
+        sub = sub[:, cols]
+        p = os.path.join(wd, "hmmbuild.model.A_0_%d" % si)
+        jobs.append((p, os.path.join(wd, "hmmbuild.input.A_0_%d.fasta" % si), sub, np.array(list(DNA + "-")), "dna", len(cols)))
+        hmm_paths.append(p); nseqs.append(hi - lo)
+        retained.append(cols.astype(np.int32)); nongaps.append((sub >= 0).sum(0).astype(np.int32))
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as ex:
+        ok = list(ex.map(_run_hmmbuild, jobs))
+    if not all(ok):
+        raise RuntimeError("hmmbuild failed for %d c1 subsets" % ok.count(False))
+    names, seqs = [n for n, _ in qs], [s.upper() for _, s in qs]
+    meta = dict(alphabet="dna", n_queries=len(seqs), H=len(hmm_paths), sumL=int(sum(len(s) for s in seqs)),
+                sumM=int(sum(len(c) for c in retained)), backbone_length=int(rows.shape[1]), seed=None, dir=wd, profiles="hmmbuild")
+    return dict(hmm_paths=hmm_paths, nseq=nseqs, names=names, seqs=seqs, retained_columns=retained, nongaps_per_column=nongaps,
+                backbone_length=int(rows.shape[1]), meta=meta)
+
+
 CONFIGS = {
-    # name: kwargs
+    # name: kwargs (SURVEY 8d); "c1" is not synthetic: make_workload dispatches it to make_workload_c1
+    "c1": dict(c1=True),
     "c2": dict(alphabet="dna", n_total=10000, n_backbone=1000, root_len=1550, decomp=10, frag_frac=0.25, frag_mean=400, seed=1),
     "c3": dict(alphabet="dna", n_total=27643, n_backbone=1000, root_len=1500, decomp=10, frag_frac=1.0, frag_mean=560, seed=2),
     "c4": dict(alphabet="amino", n_total=20000, n_backbone=800, root_len=300, decomp=10, frag_frac=0.0, frag_mean=150, seed=3, mean_blen=0.05, indel_rate=0.004),

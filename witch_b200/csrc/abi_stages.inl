@@ -155,11 +155,34 @@ static void run_wave_host_items(witch_ehmm *e, witch_queries *q, const std::vect
     run_wave<ALIGN>(e, q, e->items.p, e->group_first.p, launches, d_envsc, d_domcorr, d_cols, d_coloff, d_dbg_fwd, d_dbg_bwd, st);
 }
 
+struct LimitError : std::runtime_error { using std::runtime_error::runtime_error; };
+
+// Shared-memory limits, checked BEFORE any work of a stage call is enqueued: the kernels stage one emission row per
+// symbol that occurs in the query set (always the K canonical ones) for the whole model, so symbols x model length is
+// bounded: parser nsym*M*4 B <= ~200 KB, wave kernels nsym*ceil(M/256)*1 KB + residue staging <= ~220 KB.
+// DNA/RNA: M <= 8192 with up to 6 distinct symbols; amino (20-25 symbols): M <= ~2,000.
+static void check_limits(const witch_ehmm *e, const witch_queries *q) {
+    for (int h = 0; h < e->H; h++) {
+        const int M = e->M[h];
+        if (M > 8192) throw LimitError("model longer than 8192 nodes is not supported");
+        const int C = (M <= 1024) ? 4 : (M <= 3072) ? 8 : (M <= 3840) ? 12 : 16;
+        int T = ((M + C - 1) / C + 31) / 32 * 32;
+        if (T < 64) T = 64;
+        const size_t ps = ((size_t)q->nsym * T * C + PARSER_RED_ROWS * S_RED) * sizeof(float);
+        const size_t ws = (size_t)q->nsym * ((M + 255) / 256) * 256 * sizeof(float) + 4 * (size_t)((q->maxlen + 16) / 16 * 16) + 4 * 3 * 2056 + 4 * 800;
+        if (ps > 200 * 1024 || ws > 220 * 1024)
+            throw LimitError("model " + std::to_string(h) + " (" + std::to_string(M) + " nodes) x " + std::to_string(q->nsym) +
+                             " distinct query symbols does not fit the kernels' shared-memory emission tables (limits: " +
+                             "symbols x nodes <= ~50,000, i.e. 8192 nodes for plain DNA/RNA, ~2,000 nodes for protein)");
+    }
+}
+
 static void check_handles(witch_ehmm *e, witch_queries *q) {
     if (!e || !q) throw std::invalid_argument("null handle");
     if (e->alph != q->alph) throw std::invalid_argument("queries were digitised for another alphabet");
     if (e->device != q->device) throw std::invalid_argument("queries live on another device than the eHMM");
     CUDA_TRY(cudaSetDevice(e->device));
+    check_limits(e, q);
 }
 
 // exclusive sum / key-value sort / running maximum on the device (CUB; the host simulation build substitutes loops)
@@ -343,6 +366,8 @@ extern "C" int witch_score_dev(witch_ehmm *e, witch_queries *q, float *d_scores,
         g_launches++;
         CUDA_TRY(cudaGetLastError());
         return WITCH_OK;
+    } catch (const LimitError &ex) {
+        return fail(WITCH_ERR_LIMIT, ex.what());
     } catch (const std::invalid_argument &ex) {
         return fail(WITCH_ERR_ARG, ex.what());
     } catch (const std::exception &ex) {
@@ -366,6 +391,8 @@ extern "C" int witch_score(witch_ehmm *e, witch_queries *q, float *scores, uint8
         if (pre) CUDA_TRY(cudaMemcpy(pre, dp.p, np * sizeof(float), cudaMemcpyDeviceToHost));
         if (flags) CUDA_TRY(cudaMemcpy(flags, df.p, np, cudaMemcpyDeviceToHost));
         return WITCH_OK;
+    } catch (const LimitError &ex) {
+        return fail(WITCH_ERR_LIMIT, ex.what());
     } catch (const std::invalid_argument &ex) {
         return fail(WITCH_ERR_ARG, ex.what());
     } catch (const std::exception &ex) {
@@ -447,6 +474,8 @@ extern "C" int witch_align_dev(witch_ehmm *e, witch_queries *q, int n_pairs, con
         e->coloff.upload(co, st);
         run_wave_host_items<true>(e, q, items, nullptr, nullptr, d_cols, e->coloff.p, nullptr, nullptr, st);
         return WITCH_OK;
+    } catch (const LimitError &ex) {
+        return fail(WITCH_ERR_LIMIT, ex.what());
     } catch (const std::invalid_argument &ex) {
         return fail(WITCH_ERR_ARG, ex.what());
     } catch (const std::exception &ex) {
@@ -472,6 +501,8 @@ extern "C" int witch_align(witch_ehmm *e, witch_queries *q, int n_pairs, const i
         if (rc != WITCH_OK) return rc;
         CUDA_TRY(cudaMemcpy(cols, dc.p, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost));
         return WITCH_OK;
+    } catch (const LimitError &ex) {
+        return fail(WITCH_ERR_LIMIT, ex.what());
     } catch (const std::invalid_argument &ex) {
         return fail(WITCH_ERR_ARG, ex.what());
     } catch (const std::exception &ex) {
@@ -514,6 +545,8 @@ extern "C" int witch_debug_fwdbwd(witch_ehmm *e, witch_queries *q, int n_pairs, 
             CUDA_TRY(cudaMemcpy(bwd_nats, db.p, n_pairs * sizeof(float), cudaMemcpyDeviceToHost));
         }
         return WITCH_OK;
+    } catch (const LimitError &ex) {
+        return fail(WITCH_ERR_LIMIT, ex.what());
     } catch (const std::invalid_argument &ex) {
         return fail(WITCH_ERR_ARG, ex.what());
     } catch (const std::exception &ex) {
@@ -564,8 +597,13 @@ extern "C" int witch_graph_align(witch_ehmm *e, int nq, const int32_t *qlen, con
                                         !row_off || !rows || !row_len)) || backbone_length <= 0 || n_hmm <= 0)
             return fail(WITCH_ERR_ARG, "witch_graph_align: bad arguments");
         if (nq == 0) return WITCH_OK;
-        CUDA_TRY(cudaSetDevice(e->device));
+        if (n_hmm != e->H) return fail(WITCH_ERR_ARG, "witch_graph_align: n_hmm differs from the eHMM");
         const int np = pair_begin[nq];
+        if (np < 0 || (np > 0 && (!pair_hmm || !pair_w || !col_off || !cols))) return fail(WITCH_ERR_ARG, "witch_graph_align: missing pair arrays");
+        for (int q = 0; q < nq; q++)
+            if (pair_begin[q + 1] < pair_begin[q] || qlen[q] < 0 || res_off[q] < 0 || row_off[q] < 0) return fail(WITCH_ERR_ARG, "witch_graph_align: bad offsets");
+        for (int p = 0; p < np; p++) if (col_off[p] < 0) return fail(WITCH_ERR_ARG, "witch_graph_align: negative column offset");
+        CUDA_TRY(cudaSetDevice(e->device));
         int Lcap = 1;
         long long res_total = 0, cols_total = 0, rows_total = 0;
         for (int q = 0; q < nq; q++) {

@@ -324,7 +324,7 @@ static std::vector<SClass> s_classes(const witch_ehmm *e, const std::vector<int>
     std::map<std::pair<int, int>, std::vector<int>> m;
     for (int h : hmms) {
         const int M = e->M[h];
-        if (M > 8192) throw std::runtime_error("model longer than 8192 nodes is not supported");
+        if (M > 8192) throw std::runtime_error("model longer than 8192 nodes is not supported");   // (check_limits refuses earlier)
         // C = 16 (3,841 .. 8,192 nodes, e.g. the root of a 16S-sized decomposition): the parameter set no longer fits the
         // register file and spills to local memory -- a slow class for the few models that long, not a fast path
         int C = (M <= 1024) ? 4 : (M <= 3072) ? 8 : (M <= 3840) ? 12 : 16;

@@ -16,6 +16,7 @@ All arithmetic runs in libwitch_b200.so on the GPU; this module only shapes inpu
 the score / weight tensors on the device between the stages (plumbing). No CPU fallback.
 """
 import math
+import time
 
 import numpy as np
 
@@ -42,23 +43,33 @@ class BatchedSearch:
     index_to_hmm order == order of `hmm_paths`; taxon names are the (already renamed) query names of the reference's
     loadSubQueries (gcmm/loader.py:381-405)."""
 
-    def __init__(self, hmm_paths, num_hmms=10, use_weight=True):
+    def __init__(self, hmm_paths, num_hmms=10, use_weight=True, runtime_path=None):
         self.ehmm = api.EHMM(hmm_paths)
         self.num_hmms = int(num_hmms)
         self.use_weight = use_weight
         self.queries = None
         self.taxa = None
         self._dev = {}
+        # <outdir>/runtime_breakdown.txt of the reference (configs.py:112-116, written through Configs.runtime): one
+        # "(tag) Time to ... (s): <seconds>" line per stage, appended here in the same format when a path is given
+        self.runtime_path = runtime_path
+
+    def _runtime(self, tag, what, seconds):
+        if self.runtime_path:
+            with open(self.runtime_path, "a") as f:
+                f.write("({}) Time to {} (s): {}\n".format(tag, what, seconds))
 
     # ------------------------------------------------------------------ score
     def search(self, taxa, seqs):
         """SearchAlgorithm.search: returns nothing in the reference (results go to files); here the device score
         table is kept on `self` and also returned as numpy: (scores[n,H], reported[n,H])."""
+        t0 = time.time()
         self.taxa = list(taxa)
         self._seqs = list(seqs)
         self.queries = api.Queries(self.ehmm, seqs)
         scores, rep, pre, flags = api.score(self.ehmm, self.queries)
         self.scores, self.reported, self.pre, self.flags = scores, rep, pre, flags
+        self._runtime("gpu_score", "run all-against-all HMM scoring on the GPU", time.time() - t0)
         return scores, rep
 
     def hmmsearch_results(self, h, evalue=0.0):
@@ -82,8 +93,10 @@ class BatchedSearch:
     def writeWeights(self):
         """-> taxon_to_weights: {taxon: ((hmm_idx, weight), ...)} top num_hmms by weight (weighting.py:121-169).
         Queries without any reported HMM are absent, as in the reference."""
+        t0 = time.time()
         idx, w, cnt = api.weights_topk(self.ehmm, self.scores, self.reported, self.num_hmms, 1)
         self.top_idx, self.top_w, self.top_count = idx, w, cnt
+        self._runtime("gpu_weights", "obtain weights given bitscores", time.time() - t0)
         out = {}
         for q, t in enumerate(self.taxa):
             if cnt[q] > 0:
@@ -113,7 +126,9 @@ class BatchedSearch:
             included[t] = top
             for h, _ in top:
                 pq.append(name_to_q[t]); ph.append(h); owner.append(t)
+        t0 = time.time()
         cols = api.align(self.ehmm, self.queries, pq, ph)
+        self._runtime("gpu_align", "align queries to their weighted HMMs", time.time() - t0)
         out = {}
         for t, sw in taxon_to_weights.items():
             if len(sw) == 0:
@@ -148,7 +163,9 @@ class BatchedSearch:
         H = self.ehmm.n
         ret = [subset_to_retained_columns[h] for h in range(H)]
         ng = [subset_to_nongaps_per_column[h] for h in range(H)]
+        t0 = time.time()
         rows = api.graph_align(self.ehmm, seqs, pair_begin, pair_hmm, pair_w, cols, ret, ng, backbone_length)
+        self._runtime("gpu_graph", "merge per-HMM alignments of every query (graph DP)", time.time() - t0)
         return {t: r for t, r in zip(taxa, rows) if r}
 
     def _seq_upper(self, q):
@@ -189,7 +206,7 @@ def writeWeightsToLocal(taxon_to_weights, path):
 # ---------------------------------------------------------------------------------------------------------------
 class DevicePipeline:
     """The whole hot path with every intermediate kept in HBM (torch tensors): score -> weights/top-k -> adaptive
-    inclusion -> align. Used by bench.py and by the multi-GPU driver (witch_b200/sharding.py)."""
+    inclusion -> align. Used by bench.py through the multi-GPU driver witch_b200.sharding.run_sharded."""
 
     def __init__(self, ehmm, k=10, device=None):
         import torch
