@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libwitch_b200.so")
 SOURCES = ["witch_abi.cu", "hmm_profile.cpp"]
-DEPS = ["parser_kernel.cuh", "wave_kernels.cuh", "md_kernel.cuh", "worklist_kernels.cuh", "post_kernels.cuh", "graph_kernel.cuh", "merge_kernel.cuh", "device_types.cuh", "abi_stages.inl",
+DEPS = ["parser_kernel.cuh", "parser2_kernel.cuh", "wave_kernels.cuh", "md_kernel.cuh", "worklist_kernels.cuh", "post_kernels.cuh", "graph_kernel.cuh", "merge_kernel.cuh", "device_types.cuh", "abi_stages.inl",
         "hmm_profile.h", os.path.join("..", "..", "include", "witch_b200.h")]
 
 

@@ -223,34 +223,71 @@ static void dev_sort_items(witch_ehmm *e, const unsigned long long *kin, unsigne
 #endif
 }
 
-// The multi-domain branch for the nmd flagged regions listed in e->mdregs -> e->mdout.
-static void run_md(witch_ehmm *e, witch_queries *q, int nmd, cudaStream_t st) {
+// The multi-domain branch for the nmd flagged regions listed in e->mdregs -> e->mdout, enqueued on `st`.
+// Three kernels per batch: the region Forward matrices (one warp per region), the stochastic traces (one THREAD per region:
+// a region's 200 traces share one random-number stream and are sequential, so the parallelism is across regions), the
+// clustering (one warp per region). Scratch slots are sized per region and packed; the host orders the regions by size
+// and cuts batches that fit the scratch budget (it needs the region list for that: one read-back of 16 B per region).
+static void run_md(witch_ehmm *e, witch_queries *q, int nmd, cudaStream_t st_list, cudaStream_t st) {
     if (nmd <= 0) return;
-    const int Lcap = q->maxlen, Qcap = e->maxQ;
-    int Mcap = 0;
-    for (int m : e->M) Mcap = std::max(Mcap, m);
+    std::vector<MdRegion> regs(nmd);
+    CUDA_TRY(cudaMemcpyAsync(regs.data(), e->mdregs.p, (size_t)nmd * sizeof(MdRegion), cudaMemcpyDeviceToHost, st_list));
+    CUDA_TRY(cudaStreamSynchronize(st_list));
     const int nsp_cap = 4096;
-    const MdLayout lay = md_layout(Lcap, Qcap, Mcap, nsp_cap);
+    std::vector<long long> bytes(nmd);
+    std::vector<int> order(nmd);
+    int Qcap = 2;
+    for (int r = 0; r < nmd; r++) {
+        const int h = regs[r].h, Lr = regs[r].j0 - regs[r].i0 + 1, Qh = std::max(2, (e->M[h] - 1) / 4 + 1);
+        bytes[r] = md_layout(Lr, Qh, e->M[h], nsp_cap).total;
+        Qcap = std::max(Qcap, Qh);
+        order[r] = r;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return bytes[a] > bytes[b]; });
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-    const double budget = std::min<double>(48.0e9, 0.4 * (double)(free_b + e->mdbytes.n));
+    const long long budget = (long long)std::min<double>(64.0e9, 0.45 * (double)(free_b + e->mdbytes.n));
+    if (bytes[order[0]] > budget) throw std::runtime_error("not enough device memory for the multi-domain scratch of one region");
+    std::vector<long long> slot_off(nmd);
+    std::vector<int> batch_begin{0};
+    long long used = 0, need = 0;
+    for (int j = 0; j < nmd; j++) {
+        const long long b = bytes[order[j]];
+        if (used + b > budget) { batch_begin.push_back(j); used = 0; }
+        slot_off[j] = used;
+        used += b;
+        need = std::max(need, used);
+    }
+    batch_begin.push_back(nmd);
+    const int nbatch = (int)batch_begin.size() - 1;
+    if ((size_t)need > e->mdbytes.n) { CUDA_TRY(cudaDeviceSynchronize()); e->mdbytes.alloc((size_t)need); }
+    if ((size_t)nmd > e->mdorder.n || (size_t)2 * nbatch + 2 > e->mdcounter.n) CUDA_TRY(cudaStreamSynchronize(st));
+    e->mdorder.upload(order, st);
+    e->mdslot.upload(slot_off, st);
+    e->mdcounter.alloc((size_t)2 * nbatch + 2);
+    CUDA_TRY(cudaMemsetAsync(e->mdcounter.p, 0, ((size_t)2 * nbatch + 2) * sizeof(unsigned), st));
     const size_t smem = (size_t)MD_WARPS * 8 * Qcap * sizeof(float);   // per warp: M and D vectors of the current row
     if (smem > 200 * 1024) throw std::runtime_error("model too long for the multi-domain branch's row staging");
-    CUDA_TRY(cudaFuncSetAttribute(md_region_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 1;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, md_region_kernel, MD_WARPS * 32, smem));
-    long long grid = std::min<long long>((nmd + MD_WARPS - 1) / MD_WARPS, (long long)e->num_sms * std::max(occ, 1));
-    grid = std::max<long long>(1, std::min<long long>(grid, (long long)(budget / ((double)lay.total * MD_WARPS))));
-    if ((double)lay.total * MD_WARPS > budget) throw std::runtime_error("not enough device memory for the multi-domain scratch");
-    const size_t need = (size_t)grid * MD_WARPS * lay.total;
-    if (need > e->mdbytes.n) { CUDA_TRY(cudaStreamSynchronize(st)); e->mdbytes.alloc(need); }
-    MdWork W;
-    W.regions = e->mdregs.p; W.nregions = nmd; W.counter = e->counter.p + 32; W.scratch = (char *)e->mdbytes.p;
-    W.slot_bytes = lay.total; W.Lcap = Lcap; W.Qcap = Qcap; W.Mcap = Mcap; W.nsp_cap = nsp_cap; W.out = e->mdout.p;
+    CUDA_TRY(cudaFuncSetAttribute(md_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ1 = 1, occ3 = 1;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, md_forward_kernel, MD_WARPS * 32, smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, md_cluster_kernel, MD_WARPS * 32, 0));
     ScopedTimer tm(3, st, 0.0);
-    WITCH_LAUNCH(md_region_kernel, (int)grid, MD_WARPS * 32, smem, st)(e->view(), q->view(), W);
-    g_launches++;
-    CUDA_TRY(cudaGetLastError());
+    for (int b = 0; b < nbatch; b++) {
+        MdWork W;
+        W.regions = e->mdregs.p; W.order = e->mdorder.p; W.slot_off = e->mdslot.p; W.begin = batch_begin[b]; W.end = batch_begin[b + 1];
+        W.scratch = (char *)e->mdbytes.p; W.Qcap = Qcap; W.nsp_cap = nsp_cap; W.out = e->mdout.p;
+        const int nb = W.end - W.begin;
+        W.counter = e->mdcounter.p + 2 * b;
+        int grid = (int)std::min<long long>((nb + MD_WARPS - 1) / MD_WARPS, (long long)e->num_sms * std::max(occ1, 1));
+        WITCH_LAUNCH(md_forward_kernel, grid, MD_WARPS * 32, smem, st)(e->view(), q->view(), W);
+        WITCH_LAUNCH(md_trace_kernel, (nb + 127) / 128, 128, 0, st)(e->view(), q->view(), W);
+        W.counter = e->mdcounter.p + 2 * b + 1;
+        grid = (int)std::min<long long>((nb + MD_WARPS - 1) / MD_WARPS, (long long)e->num_sms * std::max(occ3, 1));
+        WITCH_LAUNCH(md_cluster_kernel, grid, MD_WARPS * 32, 0, st)(e->view(), q->view(), W);
+        g_launches += 3;
+        CUDA_TRY(cudaGetLastError());
+    }
 }
 
 extern "C" int witch_score_dev(witch_ehmm *e, witch_queries *q, float *d_scores, uint8_t *d_reported, float *d_pre,
@@ -323,7 +360,7 @@ extern "C" int witch_score_dev(witch_ehmm *e, witch_queries *q, float *d_scores,
             g_launches++;
             CUDA_TRY(cudaEventRecord(e->ev_fork, st));
             CUDA_TRY(cudaStreamWaitEvent(e->aux, e->ev_fork, 0));
-            run_md(e, q, nmd, e->aux);
+            run_md(e, q, nmd, st, e->aux);   // (reads the region list back on `st`, then enqueues on the side stream)
             CUDA_TRY(cudaEventRecord(e->ev_join, e->aux));
         }
         if (nA > 0) {

@@ -30,20 +30,25 @@ struct MdOut {
     float ccorr[MD_MAXC];  // sum of ln null2 over each envelope
     long long clk[4];      // device clock ticks spent in Forward / traces / clustering (WITCH_TIMING diagnostics), region size
 };
+// One batch of regions: region j of the batch is regions[order[begin + j]], its scratch slot starts at scratch +
+// slot_off[begin + j] (slots are sized per region and packed; the host cuts batches that fit the scratch budget).
 struct MdWork {
     const MdRegion *regions;
-    int nregions;
+    const int *order;
+    const long long *slot_off;
+    int begin, end;
     unsigned *counter;
     char *scratch;
-    long long slot_bytes;
-    int Lcap, Qcap, Mcap, nsp_cap;
+    int Qcap, nsp_cap;
     MdOut *out;
 };
 
-struct MdLayout { long long dp, xmx, acc, sp, asg, epc, tkb, total; };
+struct MdLayout { long long hdr, dp, xmx, acc, sp, asg, epc, tkb, total; };
+// slot of one region of Lcap residues against a model of Mcap nodes (Qcap striped vectors per row)
 __host__ __device__ inline MdLayout md_layout(int Lcap, int Qcap, int Mcap, int nsp_cap) {
     MdLayout l;
     long long o = 0;
+    l.hdr = o; o += 64;   // ints: [0] sampled domains, [1] overflow flag, [2..] clock ticks (diagnostics)
     l.dp = o; o += (long long)(Lcap + 1) * Qcap * 12 * 4;
     l.xmx = o; o += (long long)(Lcap + 1) * 8 * 4;
     l.acc = o; o += (long long)(Lcap + 4) * 4;
@@ -122,43 +127,66 @@ __device__ __forceinline__ bool md_link(int ai, int aj, int ak, int am, int bi, 
     return abs((aj - am) - (bj - bm)) <= 4;
 }
 
-constexpr int MD_WARPS = 4;   // warps per CTA
+constexpr int MD_WARPS = 4;   // warps per CTA of the warp-per-region kernels
 
-__global__ void __launch_bounds__(MD_WARPS * 32) md_region_kernel(DevEhmm E, DevQueries Qs, MdWork W) {
+// everything a kernel needs to know about region j of the batch
+struct MdCtx {
+    MdRegion R; MdOut *out;
+    int M, Q, L, Lr, K;
+    const float *tfv, *rfv;
+    const uint8_t *rd;
+    float pmove, ploop;
+    size_t RW;
+    float *dp, *xmx, *acc;
+    int *hdr, *spi, *spj, *spk, *spm, *spt, *asg, *epc, *tkb;
+};
+__device__ __forceinline__ MdCtx md_ctx(const DevEhmm &E, const DevQueries &Qs, const MdWork &W, int j) {
+    MdCtx c;
+    const int ridx = W.order[W.begin + j];
+    c.R = W.regions[ridx];
+    c.out = W.out + ridx;
+    c.M = E.M[c.R.h]; c.Q = E.oQ[c.R.h];
+    c.tfv = E.otfv + E.otoff[c.R.h];
+    c.rfv = E.orfv + E.oroff[c.R.h];
+    c.L = Qs.len[c.R.q]; c.Lr = c.R.j0 - c.R.i0 + 1;
+    c.K = (E.Kp == 29) ? 20 : 4;
+    c.rd = Qs.dsq + Qs.off[c.R.q] + (c.R.i0 - 1);   // rd[i-1] = dense code of residue i of the region
+    c.pmove = 3.0f / ((float)c.L + 3.0f); c.ploop = 1.0f - c.pmove;
+    c.RW = (size_t)c.Q * 12;                       // floats per row: [q][M|D|I][4]
+    const MdLayout lay = md_layout(c.Lr, c.Q, c.M, W.nsp_cap);
+    char *slot = W.scratch + W.slot_off[W.begin + j];
+    c.hdr = (int *)(slot + lay.hdr);
+    c.dp = (float *)(slot + lay.dp);
+    c.xmx = (float *)(slot + lay.xmx);           // 8 floats per row: E N J B C SCALE - -
+    c.acc = (float *)(slot + lay.acc);
+    c.spi = (int *)(slot + lay.sp); c.spj = c.spi + W.nsp_cap; c.spk = c.spj + W.nsp_cap; c.spm = c.spk + W.nsp_cap; c.spt = c.spm + W.nsp_cap;
+    c.asg = (int *)(slot + lay.asg);
+    c.epc = (int *)(slot + lay.epc);
+    c.tkb = (int *)(slot + lay.tkb);
+    return c;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Kernel 1: the region's Forward matrix, HMMER's arithmetic operation by operation. One warp per region.
+__global__ void __launch_bounds__(MD_WARPS * 32) md_forward_kernel(DevEhmm E, DevQueries Qs, MdWork W) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const unsigned FULL = 0xffffffffu;
-    __shared__ float s_null2[MD_WARPS][32];
-    __shared__ int s_dom[MD_WARPS][MD_MAXDOM][4];
-    __shared__ int s_sig[MD_WARPS][MD_MAXSIG][6];     // i, j, k, m, count, cluster order
-    __shared__ unsigned s_bits[MD_WARPS][8];
-    const MdLayout lay = md_layout(W.Lcap, W.Qcap, W.Mcap, W.nsp_cap);
-    char *slot = W.scratch + ((long long)blockIdx.x * MD_WARPS + w) * W.slot_bytes;
-    float *dp = (float *)(slot + lay.dp);
-    float *xmx = (float *)(slot + lay.xmx);     // 8 floats per row: E N J B C SCALE - -
-    float *acc = (float *)(slot + lay.acc);
-    int *spi = (int *)(slot + lay.sp), *spj = spi + W.nsp_cap, *spk = spj + W.nsp_cap, *spm = spk + W.nsp_cap, *spt = spm + W.nsp_cap;
-    int *asg = (int *)(slot + lay.asg);
-    int *epc = (int *)(slot + lay.epc);
-    const int K = (E.Kp == 29) ? 20 : 4;
     WITCH_DYN_SMEM(float, md_smem);   // per warp: the current row's M and D vectors, [Qcap][4] each
     float *sMv = md_smem + (size_t)w * 8 * W.Qcap, *sDv = sMv + (size_t)4 * W.Qcap;
-    int *tkb = (int *)(slot + lay.tkb);   // model nodes of the emitting states of the running domain
-
     for (;;) {
         int item = 0;
         if (lane == 0) item = (int)atomicAdd(W.counter, 1u);
         item = __shfl_sync(FULL, item, 0);
-        if (item >= W.nregions) break;
-        const MdRegion R = W.regions[item];
-        MdOut *out = W.out + item;
-        const int M = E.M[R.h], Q = E.oQ[R.h];
-        const float *tfv = E.otfv + E.otoff[R.h];
-        const float *rfv = E.orfv + E.oroff[R.h];
-        const int L = Qs.len[R.q], Lr = R.j0 - R.i0 + 1;
-        const uint8_t *rd = Qs.dsq + Qs.off[R.q] + (R.i0 - 1);   // rd[i-1] = dense code of residue i of the region
-        const float pmove = 3.0f / ((float)L + 3.0f), ploop = 1.0f - pmove;
-        const size_t RW = (size_t)Q * 12;   // floats per row: [q][M|D|I][4]
-
+        if (item >= W.end - W.begin) break;
+        const MdCtx cx = md_ctx(E, Qs, W, item);
+        const MdRegion R = cx.R;
+        const int M = cx.M, Q = cx.Q, Lr = cx.Lr;
+        const float *tfv = cx.tfv, *rfv = cx.rfv;
+        const uint8_t *rd = cx.rd;
+        const float pmove = cx.pmove, ploop = cx.ploop;
+        const size_t RW = cx.RW;
+        float *dp = cx.dp, *xmx = cx.xmx;
+        (void)R;
         const long long clk0 = clock64();
         // ====================== Forward over the region (multihit, length model of the whole sequence) ======================
         // A row's M and D vectors are staged in shared memory ([q][4] each) for the serial part; the global matrix row
@@ -288,202 +316,183 @@ __global__ void __launch_bounds__(MD_WARPS * 32) md_region_kernel(DevEhmm E, Dev
             __syncwarp();
         }
 
-        const long long clk1 = clock64();
-        // ====================== 200 stochastic traces, null2 by trace, sampled domains ======================
-        for (int p = lane; p <= Lr + 1; p += 32) acc[p] = 0.f;
-        unsigned rng = md_mix3(42u, 87654321u, 12345678u);
-        if (rng == 0u) rng = 42u;
-        int nsp = 0, oflow = 0;
+        if (lane == 0) { cx.hdr[2] = (int)((clock64() - clk0) >> 10); }
         __syncwarp();
-        enum { tM = 1, tD = 2, tI = 3, tS = 4, tN = 5, tB = 6, tE = 7, tC = 8, tJ = 10 };
-        for (int t = 0; t < MD_NSAMPLES; t++) {
-            // Lane 0 walks the trace backwards on its own and calls the warp in at three kinds of events: an E state to
-            // resolve (a choice among all M/D cells of a row), a finished domain (null2 of its states, per-residue
-            // accumulation), the end of the trace. Its running domain: sqfrom..sqto, hfrom..hto, Ld emitting states whose
-            // model nodes are listed in tkb[].
-            int i = Lr, k = 0, s0 = tC, ndom = 0, hi = Lr;
-            int sqto = 0, sqfrom = 0, hto = 0, hfrom = 0, Ld = 0;
-            int cq = 0, cr = 0;   // (k-1) % Q and (k-1) / Q of the current node, kept incrementally (no divisions per step)
-            for (;;) {
-                int ev = 0;
-                if (lane == 0) {
-                    while (ev == 0) {
-                        if (s0 == tE) { ev = 1; break; }
-                        if (s0 == tS) { ev = 3; break; }
-                        int s1;
-                        const float *x1 = xmx + (size_t)i * 8, *x0 = xmx + (size_t)(i > 0 ? i - 1 : 0) * 8;
-                        float path[4];
-                        if (s0 == tM) {
-                            k--;
-                            const int q = cq, r = cr;   // = k % Q, k / Q of the decremented k
-                            if (--cq < 0) { cq += Q; cr--; }
-                            const float *tp = tfv + (size_t)q * 28 + r;
-                            const float *pr = dp + (size_t)(i - 1) * RW;
-                            float mp = 0.f, dd = 0.f, ip = 0.f;
-                            if (q > 0) { const float *v = pr + (size_t)(q - 1) * 12 + r; mp = v[0]; dd = v[4]; ip = v[8]; }
-                            else if (r > 0) { const float *v = pr + (size_t)(Q - 1) * 12 + r - 1; mp = v[0]; dd = v[4]; ip = v[8]; }
-                            const float xb = x0[3], t0 = tp[0], t1 = tp[4], t2 = tp[8], t3 = tp[12];
-                            // the path most likely continues on the diagonal: pull the cells of the next steps towards L1
-                            if (i >= 5) {
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Kernel 2: the 200 stochastic traces of a region, its position-specific null2 and its sampled domains. The walk is
+// sequential by nature (one random-number stream per region), so ONE THREAD per region: the parallelism is across the
+// regions of the batch (ordered by size, so the lanes of a warp walk matrices of similar shape).
+__global__ void __launch_bounds__(128) md_trace_kernel(DevEhmm E, DevQueries Qs, MdWork W) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= W.end - W.begin) return;
+    const MdCtx cx = md_ctx(E, Qs, W, j);
+    const int Q = cx.Q, Lr = cx.Lr, K = cx.K;
+    const float *tfv = cx.tfv, *rfv = cx.rfv, *dp = cx.dp, *xmx = cx.xmx;
+    const uint8_t *rd = cx.rd;
+    const float pmove = cx.pmove, ploop = cx.ploop;
+    const size_t RW = cx.RW;
+    float *acc = cx.acc;
+    const long long clk0 = clock64();
+    enum { tM = 1, tD = 2, tI = 3, tS = 4, tN = 5, tB = 6, tE = 7, tC = 8, tJ = 10 };
+    for (int p = 0; p <= Lr + 1; p++) acc[p] = 0.f;
+    unsigned rng = md_mix3(42u, 87654321u, 12345678u);
+    if (rng == 0u) rng = 42u;
+    int nsp = 0, oflow = 0;
+    for (int t = 0; t < MD_NSAMPLES; t++) {
+        int i = Lr, k = 0, s0 = tC, ndom = 0, hi = Lr;
+        int sqto = 0, sqfrom = 0, hto = 0, hfrom = 0, Ld = 0;
+        int cq = 0, cr = 0;   // (k-1) % Q and (k-1) / Q of the current node, kept incrementally
+        double sums[20];      // sum over the running domain's emitting states of the match odds of every residue
+        while (s0 != tS) {
+            int s1;
+            const float *x1 = xmx + (size_t)i * 8, *x0 = xmx + (size_t)(i > 0 ? i - 1 : 0) * 8;
+            float path[4];
+            if (s0 == tM) {
+                k--;
+                const int q = cq, r = cr;   // = k % Q, k / Q of the decremented k
+                if (--cq < 0) { cq += Q; cr--; }
+                const float *tp = tfv + (size_t)q * 28 + r;
+                const float *pr = dp + (size_t)(i - 1) * RW;
+                float mp = 0.f, dd = 0.f, ip = 0.f;
+                if (q > 0) { const float *v = pr + (size_t)(q - 1) * 12 + r; mp = v[0]; dd = v[4]; ip = v[8]; }
+                else if (r > 0) { const float *v = pr + (size_t)(Q - 1) * 12 + r - 1; mp = v[0]; dd = v[4]; ip = v[8]; }
+                path[0] = md_mul(x0[3], tp[0]); path[1] = md_mul(mp, tp[4]); path[2] = md_mul(ip, tp[8]); path[3] = md_mul(dd, tp[12]);
+                const int c = md_choose(rng, path, 4);
+                s1 = (c == 0) ? tB : (c == 1) ? tM : (c == 2) ? tI : tD;
+                i--;
+            } else if (s0 == tD) {
+                k--;
+                const int q = cq, r = cr;
+                if (--cq < 0) { cq += Q; cr--; }
+                const float *crow = dp + (size_t)i * RW;
+                float mp = 0.f, dd = 0.f, tmd = 0.f, tdd = 0.f;
+                if (q > 0) {
+                    mp = crow[(size_t)(q - 1) * 12 + r]; dd = crow[(size_t)(q - 1) * 12 + 4 + r];
+                    tmd = tfv[(size_t)(q - 1) * 28 + 16 + r]; tdd = tfv[(size_t)Q * 28 + (size_t)(q - 1) * 4 + r];
+                } else if (r > 0) {
+                    mp = crow[(size_t)(Q - 1) * 12 + r - 1]; dd = crow[(size_t)(Q - 1) * 12 + 4 + r - 1];
+                    tmd = tfv[(size_t)(Q - 1) * 28 + 16 + r - 1]; tdd = tfv[(size_t)Q * 28 + (size_t)(Q - 1) * 4 + r - 1];
+                }
+                path[0] = md_mul(mp, tmd); path[1] = md_mul(dd, tdd);
+                s1 = md_choose(rng, path, 2) == 0 ? tM : tD;
+            } else if (s0 == tI) {
+                const int q = cq, r = cr;
+                const float *pr = dp + (size_t)(i - 1) * RW + (size_t)q * 12 + r;
+                path[0] = md_mul(pr[0], tfv[(size_t)q * 28 + 20 + r]);
+                path[1] = md_mul(pr[8], tfv[(size_t)q * 28 + 24 + r]);
+                s1 = md_choose(rng, path, 2) == 0 ? tM : tI;
+                i--;
+            } else if (s0 == tN) {
+                s1 = (i == 0) ? tS : tN;
+            } else if (s0 == tC) {
+                path[0] = md_mul(ploop, x0[4]);
+                path[1] = md_mul(md_mul(0.5f, x1[0]), x1[5]);
+                s1 = md_choose(rng, path, 2) == 0 ? tC : tE;
+            } else if (s0 == tJ) {
+                path[0] = md_mul(ploop, x0[2]);
+                path[1] = md_mul(md_mul(0.5f, x1[0]), x1[5]);
+                s1 = md_choose(rng, path, 2) == 0 ? tJ : tE;
+            } else if (s0 == tB) {
+                path[0] = md_mul(pmove, x1[1]);
+                path[1] = md_mul(pmove, x1[2]);
+                s1 = md_choose(rng, path, 2) == 0 ? tN : tJ;
+            } else {   // E: one roll against the running sum over all M/D cells of row i, in HMMER's striped order
+                const double roll = md_rand(rng);
+                const float norm = 1.0f / x1[0];
+                const float *row = dp + (size_t)i * RW;
+                double sum = 0.0;
+                int kk = 1;
+                s1 = tM;
+                bool found = false;
+                for (int q = 0; q < Q && !found; q++) {
+                    const float4 m4 = *reinterpret_cast<const float4 *>(row + (size_t)q * 12), d4 = *reinterpret_cast<const float4 *>(row + (size_t)q * 12 + 4);
+                    const float v8[8] = {m4.x, m4.y, m4.z, m4.w, d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
-                                for (int dstep = 2; dstep <= 4; dstep += 2) {
-                                    int qd = q - 1 - dstep, rd2 = r;
-                                    if (qd < 0) { qd += Q; rd2--; }
-                                    if (rd2 >= 0) {
-                                        md_prefetch(dp + (size_t)(i - 1 - dstep) * RW + (size_t)qd * 12 + rd2);
-                                        md_prefetch(tfv + (size_t)(qd + 1 < Q ? qd + 1 : 0) * 28);
-                                    }
-                                }
-                            }
-                            path[0] = md_mul(xb, t0); path[1] = md_mul(mp, t1); path[2] = md_mul(ip, t2); path[3] = md_mul(dd, t3);
-                            const int c = md_choose(rng, path, 4);
-                            s1 = (c == 0) ? tB : (c == 1) ? tM : (c == 2) ? tI : tD;
-                            i--;
-                        } else if (s0 == tD) {
-                            k--;
-                            const int q = cq, r = cr;
-                            if (--cq < 0) { cq += Q; cr--; }
-                            const float *crow = dp + (size_t)i * RW;
-                            float mp = 0.f, dd = 0.f, tmd = 0.f, tdd = 0.f;
-                            if (q > 0) {
-                                mp = crow[(size_t)(q - 1) * 12 + r]; dd = crow[(size_t)(q - 1) * 12 + 4 + r];
-                                tmd = tfv[(size_t)(q - 1) * 28 + 16 + r]; tdd = tfv[(size_t)Q * 28 + (size_t)(q - 1) * 4 + r];
-                            } else if (r > 0) {
-                                mp = crow[(size_t)(Q - 1) * 12 + r - 1]; dd = crow[(size_t)(Q - 1) * 12 + 4 + r - 1];
-                                tmd = tfv[(size_t)(Q - 1) * 28 + 16 + r - 1]; tdd = tfv[(size_t)Q * 28 + (size_t)(Q - 1) * 4 + r - 1];
-                            }
-                            path[0] = md_mul(mp, tmd); path[1] = md_mul(dd, tdd);
-                            s1 = md_choose(rng, path, 2) == 0 ? tM : tD;
-                        } else if (s0 == tI) {
-                            const int q = cq, r = cr;
-                            const float *pr = dp + (size_t)(i - 1) * RW + (size_t)q * 12 + r;
-                            path[0] = md_mul(pr[0], tfv[(size_t)q * 28 + 20 + r]);
-                            path[1] = md_mul(pr[8], tfv[(size_t)q * 28 + 24 + r]);
-                            s1 = md_choose(rng, path, 2) == 0 ? tM : tI;
-                            i--;
-                        } else if (s0 == tN) {
-                            s1 = (i == 0) ? tS : tN;
-                        } else if (s0 == tC) {
-                            path[0] = md_mul(ploop, x0[4]);
-                            path[1] = md_mul(md_mul(0.5f, x1[0]), x1[5]);
-                            s1 = md_choose(rng, path, 2) == 0 ? tC : tE;
-                        } else if (s0 == tJ) {
-                            path[0] = md_mul(ploop, x0[2]);
-                            path[1] = md_mul(md_mul(0.5f, x1[0]), x1[5]);
-                            s1 = md_choose(rng, path, 2) == 0 ? tJ : tE;
-                        } else {   // B
-                            path[0] = md_mul(pmove, x1[1]);
-                            path[1] = md_mul(pmove, x1[2]);
-                            s1 = md_choose(rng, path, 2) == 0 ? tN : tJ;
-                        }
-                        if (s1 == tM || s1 == tI) {   // (3.1b2 counts a residue emitted by I_k in the MATCH cell of node k)
-                            if (s1 == tM) { if (sqto == 0) { sqto = i; hto = k; } sqfrom = i; hfrom = k; }
-                            tkb[Ld++] = k;
-                        }
-                        if ((s1 == tN || s1 == tJ || s1 == tC) && s1 == s0) i--;
-                        s0 = s1;
-                        if (s1 == tB) ev = 2;
+                    for (int r = 0; r < 8; r++) {
+                        sum += (double)md_mul(v8[r], norm);
+                        if (!found && sum > roll) { kk = (r & 3) * Q + q + 1; s1 = (r < 4) ? tM : tD; found = true; }
                     }
                 }
-                ev = __shfl_sync(FULL, ev, 0);
-                if (ev == 3) break;
-                if (ev == 1) {
-                    // choice among all M/D cells of row i in striped order, cooperatively: each lane sums a contiguous
-                    // range of vectors, a prefix scan locates the lane that crosses the roll, that lane finds the cell
-                    i = __shfl_sync(FULL, i, 0);
-                    double roll = 0.0;
-                    if (lane == 0) roll = md_rand(rng);
-                    roll = __shfl_sync(FULL, roll, 0);
-                    const float norm = 1.0f / xmx[(size_t)i * 8];
-                    const float *row = dp + (size_t)i * RW;
-                    const int per = (Q + 31) / 32, q0 = min(lane * per, Q), q1 = min(q0 + per, Q);
-                    double part = 0.0;
-                    for (int q = q0; q < q1; q++)
-#pragma unroll
-                        for (int r = 0; r < 8; r++) part += (double)md_mul(row[(size_t)q * 12 + r], norm);
-                    double incl = part;
-                    for (int o = 1; o < 32; o <<= 1) { const double u = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += u; }
-                    const unsigned hit = __ballot_sync(FULL, incl > roll);
-                    int kk = 1, ss = tM;
-                    if (hit != 0u) {
-                        const int src = __ffs((int)hit) - 1;
-                        if (lane == src) {
-                            double sum = incl - part;
-                            bool found = false;
-                            for (int q = q0; q < q1 && !found; q++)
-                                for (int r = 0; r < 8; r++) {
-                                    sum += (double)md_mul(row[(size_t)q * 12 + r], norm);
-                                    if (sum > roll) { kk = (r & 3) * Q + q + 1; ss = (r < 4) ? tM : tD; found = true; break; }
-                                }
-                            if (!found) { kk = (q1 - 1) + 1; ss = tM; }
-                        }
-                        kk = __shfl_sync(FULL, kk, src); ss = __shfl_sync(FULL, ss, src);
-                    }
-                    // a new domain starts (seen from its end)
-                    k = kk; s0 = ss;
-                    cq = (kk - 1) % Q; cr = (kk - 1) / Q;
-                    sqto = 0; sqfrom = 0; hto = 0; hfrom = 0; Ld = 0;
-                    if (ss == tM) { sqto = i; hto = kk; sqfrom = i; hfrom = kk; if (lane == 0) tkb[0] = kk; Ld = 1; }
-                    continue;
-                }
-                // ev == 2: domain sqfrom..sqto complete: null2 odds of its states, accumulated per residue
-                sqfrom = __shfl_sync(FULL, sqfrom, 0); sqto = __shfl_sync(FULL, sqto, 0);
-                hfrom = __shfl_sync(FULL, hfrom, 0); hto = __shfl_sync(FULL, hto, 0); Ld = __shfl_sync(FULL, Ld, 0);
-                __syncwarp();
-                {
-                    const float nrm = (float)(1.0 / (double)(float)Ld);
-                    for (int x = 0; x < K; x++) {
-                        double sx = 0.0;
-                        for (int z = lane; z < Ld; z += 32) {
-                            const int kz = tkb[z] - 1;
-                            sx += (double)rfv[((size_t)x * Q + (kz % Q)) * 4 + kz / Q];
-                        }
-                        for (int o = 16; o > 0; o >>= 1) sx += __shfl_xor_sync(FULL, sx, o);
-                        if (lane == 0) s_null2[w][x] = (float)(sx * (double)nrm);
-                    }
-                }
-                __syncwarp();
-                for (int p = sqto + 1 + lane; p <= hi; p += 32) acc[p] = md_add(acc[p], 1.0f);
-                for (int p = sqfrom + 1 + lane; p <= sqto; p += 32) {
+                k = kk;
+                cq = (kk - 1) % Q; cr = (kk - 1) / Q;
+                sqto = 0; sqfrom = 0; hto = 0; hfrom = 0; Ld = 0;   // a new domain starts (seen from its end)
+                for (int x = 0; x < K; x++) sums[x] = 0.0;
+            }
+            if (s1 == tM || s1 == tI) {   // (3.1b2 counts a residue emitted by I_k in the MATCH cell of node k)
+                if (s1 == tM) { if (sqto == 0) { sqto = i; hto = k; } sqfrom = i; hfrom = k; }
+                Ld++;
+                for (int x = 0; x < K; x++) sums[x] += (double)rfv[((size_t)x * Q + cq) * 4 + cr];
+            } else if (s1 == tB) {
+                // domain sqfrom..sqto complete: null2 odds of its states, accumulated per residue
+                float null2[20];
+                const float nrm = (float)(1.0 / (double)(float)Ld);
+                for (int x = 0; x < K; x++) null2[x] = (float)(sums[x] * (double)nrm);
+                for (int p = sqto + 1; p <= hi; p++) acc[p] = md_add(acc[p], 1.0f);
+                for (int p = sqfrom + 1; p <= sqto; p++) {
                     const int code = Qs.symrow[rd[p - 1]];
                     float v;
-                    if (code < K) v = s_null2[w][code];
+                    if (code < K) v = null2[code];
                     else {
                         const unsigned mask = md_degen_mask(E.Kp, code);
                         float sg = 0.f; int n = 0;
-                        for (int x = 0; x < K; x++) if (mask >> x & 1u) { sg += s_null2[w][x]; n++; }
+                        for (int x = 0; x < K; x++) if (mask >> x & 1u) { sg += null2[x]; n++; }
                         v = n ? sg / (float)n : 1.0f;
                     }
                     acc[p] = md_add(acc[p], v);
                 }
                 hi = sqfrom;   // (HMMER gives residue sqfrom the neutral 1.0 as well)
-                if (ndom < MD_MAXDOM && lane == 0) { s_dom[w][ndom][0] = sqfrom; s_dom[w][ndom][1] = sqto; s_dom[w][ndom][2] = hfrom; s_dom[w][ndom][3] = hto; }
-                ndom++;
-                sqto = 0; sqfrom = 0; hto = 0; hfrom = 0; Ld = 0;
-                __syncwarp();
+                if (ndom < MD_MAXDOM && nsp + ndom < W.nsp_cap) {
+                    const int z = nsp + ndom;
+                    cx.spi[z] = sqfrom + cx.R.i0 - 1; cx.spj[z] = sqto + cx.R.i0 - 1; cx.spk[z] = hfrom; cx.spm[z] = hto; cx.spt[z] = t;
+                    ndom++;
+                } else oflow = 1;
             }
-            for (int p = 1 + lane; p <= hi; p += 32) acc[p] = md_add(acc[p], 1.0f);
-            // the trace's domains enter the ensemble in sequence order (they were found last to first)
-            if (ndom > MD_MAXDOM) { oflow = 1; ndom = MD_MAXDOM; }
-            __syncwarp();
-            for (int d = lane; d < ndom; d += 32) {
-                const int z = nsp + d;
-                if (z < W.nsp_cap) {
-                    const int *v = s_dom[w][ndom - 1 - d];
-                    spi[z] = v[0] + R.i0 - 1; spj[z] = v[1] + R.i0 - 1; spk[z] = v[2]; spm[z] = v[3]; spt[z] = t;
-                }
-            }
-            nsp += ndom;
-            if (nsp > W.nsp_cap) { oflow = 1; nsp = W.nsp_cap; }
-            __syncwarp();
+            if ((s1 == tN || s1 == tJ || s1 == tC) && s1 == s0) i--;
+            s0 = s1;
         }
+        for (int p = 1; p <= hi; p++) acc[p] = md_add(acc[p], 1.0f);
+        // the trace's domains enter the ensemble in sequence order (they were found last to first): reverse the segment
+        for (int a = nsp, b = nsp + ndom - 1; a < b; a++, b--) {
+            int tmp;
+            tmp = cx.spi[a]; cx.spi[a] = cx.spi[b]; cx.spi[b] = tmp; tmp = cx.spj[a]; cx.spj[a] = cx.spj[b]; cx.spj[b] = tmp;
+            tmp = cx.spk[a]; cx.spk[a] = cx.spk[b]; cx.spk[b] = tmp; tmp = cx.spm[a]; cx.spm[a] = cx.spm[b]; cx.spm[b] = tmp;
+        }
+        nsp += ndom;
+    }
+    cx.hdr[0] = nsp; cx.hdr[1] = oflow; cx.hdr[3] = (int)((clock64() - clk0) >> 10);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Kernel 3: ln of the mean null2 odds, single-linkage clustering of the sampled domains, envelopes. One warp per region.
+__global__ void __launch_bounds__(MD_WARPS * 32) md_cluster_kernel(DevEhmm E, DevQueries Qs, MdWork W) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned FULL = 0xffffffffu;
+    __shared__ int s_sig[MD_WARPS][MD_MAXSIG][6];     // i, j, k, m, count, cluster order
+    __shared__ unsigned s_bits[MD_WARPS][8];
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = (int)atomicAdd(W.counter, 1u);
+        item = __shfl_sync(FULL, item, 0);
+        if (item >= W.end - W.begin) break;
+        const MdCtx cx = md_ctx(E, Qs, W, item);
+        const MdRegion R = cx.R;
+        MdOut *out = cx.out;
+        const int M = cx.M, Lr = cx.Lr;
+        float *acc = cx.acc;
+        int *spi = cx.spi, *spj = cx.spj, *spk = cx.spk, *spm = cx.spm, *spt = cx.spt, *asg = cx.asg, *epc = cx.epc;
+        const int nsp = cx.hdr[0];
+        int oflow = cx.hdr[1];
+        const long long clk1 = 0, clk0 = 0, clk2 = clock64();
+        (void)clk1; (void)clk0;
         // ln of the mean null2 odds per residue -> acc[]; sum over the region
         float regc = 0.f;
         for (int p = 1 + lane; p <= Lr; p += 32) { const float v = logf(acc[p] / (float)MD_NSAMPLES); acc[p] = v; regc += v; }
         for (int o = 16; o > 0; o >>= 1) regc += __shfl_xor_sync(FULL, regc, o);
         __syncwarp();
 
-        const long long clk2 = clock64();
         // ====================== single-linkage clustering of the sampled domains ======================
         for (int a = lane; a < nsp; a += 32) asg[a] = a;
         __syncwarp();
@@ -585,7 +594,7 @@ __global__ void __launch_bounds__(MD_WARPS * 32) md_region_kernel(DevEhmm E, Dev
                 } else fl = 4;
             }
             out->nclust = nout; out->flags = fl; out->regcorr = regc;
-            out->clk[0] = clk1 - clk0; out->clk[1] = clk2 - clk1; out->clk[2] = clock64() - clk2; out->clk[3] = ((long long)Lr << 32) | (unsigned)M;
+            out->clk[0] = (long long)cx.hdr[2] << 10; out->clk[1] = (long long)cx.hdr[3] << 10; out->clk[2] = clock64() - clk2; out->clk[3] = ((long long)Lr << 32) | (unsigned)M;
         }
         __syncwarp();
     }

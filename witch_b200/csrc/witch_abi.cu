@@ -20,6 +20,7 @@
 #include "device_types.cuh"
 #include "hmm_profile.h"
 #include "parser_kernel.cuh"
+#include "parser2_kernel.cuh"
 #include "wave_kernels.cuh"
 #include "md_kernel.cuh"
 #include "worklist_kernels.cuh"
@@ -114,6 +115,9 @@ struct witch_ehmm {
     DevBuf<unsigned long long> keys, keys2;
     DevBuf<WaveItem> items, items2;
     DevBuf<MdRegion> mdregs;
+    DevBuf<int> mdorder;
+    DevBuf<long long> mdslot;
+    DevBuf<unsigned> mdcounter;
     DevBuf<MdOut> mdout;
     DevBuf<WlDesc> desc;
     DevBuf<long long> coloff;
@@ -353,6 +357,32 @@ static void launch_parser(const witch_ehmm *e, const witch_queries *q, int T, Pa
     CUDA_TRY(cudaGetLastError());
 }
 
+template <int C, int MAXT, int MINB, bool PSMEM>
+static void launch_parser2(const witch_ehmm *e, const witch_queries *q, int T, ParserWork wk, cudaStream_t st, int maxgrid) {
+    const size_t smem = ((size_t)(q->nsym + (PSMEM ? P2_NROWS : 0)) * T * C + PARSER_RED_ROWS * S_RED) * sizeof(float);
+    if (smem > 220 * 1024) throw std::runtime_error("emission + parameter tables do not fit shared memory");
+    auto kern = mh_parser2_kernel<C, MAXT, MINB, PSMEM>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, smem));
+    if (occ < 1) throw std::runtime_error("parser kernel cannot be resident (registers/shared memory)");
+    const long long nitems = (long long)wk.nh * ((wk.nq + 1) / 2);
+    const int grid = (int)std::min<long long>(std::min<long long>(nitems, (long long)e->num_sms * occ), maxgrid);
+    WITCH_LAUNCH(kern, grid, T, smem, st)(e->view(), q->view(), wk);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+}
+
+// Parser generation: 1 = one query per CTA (parser_kernel.cuh), 2 = two queries per CTA in packed f32x2 registers with the
+// transition parameters in registers, 3 = the same with the parameters in shared memory (parser2_kernel.cuh).
+#ifndef WITCH_PARSER_DEFAULT
+#define WITCH_PARSER_DEFAULT 1
+#endif
+static int parser_generation() {
+    static const int g = [] { const char *s = getenv("WITCH_PARSER"); return s ? atoi(s) : WITCH_PARSER_DEFAULT; }();
+    return g;
+}
+
 // Runs the multihit parser for all (query in qsel) x (hmm in hsel); results in e->parse [n_queries*H].
 static void run_parser(witch_ehmm *e, witch_queries *q, const std::vector<int> &qsel, const std::vector<int> &hsel,
                        float *d_dbg_bwd, cudaStream_t st) {
@@ -363,7 +393,7 @@ static void run_parser(witch_ehmm *e, witch_queries *q, const std::vector<int> &
     e->i1.upload(qorder, st);
     const int Lcap = q->maxlen + 1;
     int maxgrid = e->num_sms * 8;
-    e->scratch.alloc((size_t)maxgrid * PARSER_SCRATCH_ROWS * (size_t)((Lcap + 4) & ~3) + 64);
+    e->scratch.alloc((size_t)maxgrid * 2 * PARSER_SCRATCH_ROWS * (size_t)((Lcap + 4) & ~3) + 64);   // (two queries per CTA in generation 2/3)
     e->counter.alloc(64);
     auto classes = s_classes(e, hsel);
     std::vector<int> allh;
@@ -391,6 +421,20 @@ static void run_parser(witch_ehmm *e, witch_queries *q, const std::vector<int> &
         wk.Lcap = Lcap; wk.scratch = e->scratch.p; wk.counter = e->counter.p + ci; wk.out = e->parse.p;
         wk.dbg_bwd = d_dbg_bwd;
         const int T = classes[ci].T;
+        const int gen = d_dbg_bwd ? 1 : parser_generation();
+        if (gen >= 2 && (classes[ci].C == 4 || classes[ci].C == 8) && (classes[ci].C == 4 ? T <= 512 : T <= 384)) {
+            const bool ps = gen == 3;   // (gen 4: register variant at 2 CTAs/SM, experiment)
+            if (classes[ci].C == 4) {
+                if (T <= 256) { if (ps) launch_parser2<4, 256, 2, true>(e, q, T, wk, st, maxgrid); else launch_parser2<4, 256, 2, false>(e, q, T, wk, st, maxgrid); }
+                else { if (ps) launch_parser2<4, 512, 1, true>(e, q, T, wk, st, maxgrid); else launch_parser2<4, 512, 1, false>(e, q, T, wk, st, maxgrid); }
+            } else {
+                if (T <= 224 && ps) launch_parser2<8, 224, 2, true>(e, q, T, wk, st, maxgrid);   // 146 registers available at 2 CTAs/SM
+                else if (T <= 224 && gen == 4) launch_parser2<8, 224, 2, false>(e, q, T, wk, st, maxgrid);   // experiment: register variant capped for 2 CTAs/SM
+                else if (T <= 256) { if (ps) launch_parser2<8, 256, 2, true>(e, q, T, wk, st, maxgrid); else launch_parser2<8, 256, 1, false>(e, q, T, wk, st, maxgrid); }
+                else { if (ps) launch_parser2<8, 384, 1, true>(e, q, T, wk, st, maxgrid); else launch_parser2<8, 384, 1, false>(e, q, T, wk, st, maxgrid); }
+            }
+            continue;
+        }
         switch (classes[ci].C) {
             case 4: if (T <= 256) launch_parser<4, 256, 2>(e, q, T, wk, st, maxgrid); else launch_parser<4, 512, 1>(e, q, T, wk, st, maxgrid); break;
             case 8: if (T <= 256) launch_parser<8, 256, 2>(e, q, T, wk, st, maxgrid); else launch_parser<8, 384, 1>(e, q, T, wk, st, maxgrid); break;
