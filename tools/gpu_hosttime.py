@@ -8,6 +8,10 @@ import torch
 import synth
 import witch_b200 as wb
 from witch_b200.gcmm import DevicePipeline
+from witch_b200 import _lib
+if os.environ.get("PERF_LIB"):
+    _lib.LIB_PATH = os.path.join(ROOT, os.environ["PERF_LIB"])
+nrep = int(os.environ.get("HOSTTIME_REPS", "3"))
 cfg = sys.argv[1] if len(sys.argv) > 1 else "c2"
 ns = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 wl = synth.make_workload("/tmp/witch_b200_bench", **synth.CONFIGS[cfg])
@@ -16,7 +20,7 @@ ids = np.sort(np.argsort(-L, kind="stable")[0::ns])
 seqs = [wl["seqs"][i] for i in ids]
 E = wb.EHMM(wl["hmm_paths"])
 pipe = DevicePipeline(E, k=10)
-for it in range(3):
+for it in range(nrep):
     t0 = time.perf_counter()
     Q = wb.Queries(E, seqs)
     t1 = time.perf_counter()

@@ -246,7 +246,7 @@ static void run_md(witch_ehmm *e, witch_queries *q, int nmd, cudaStream_t st_lis
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return bytes[a] > bytes[b]; });
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-    const long long budget = (long long)std::min<double>(64.0e9, 0.45 * (double)(free_b + e->mdbytes.n));
+    const long long budget = (long long)std::min<double>(110.0e9, 0.6 * (double)(free_b + e->mdbytes.n));
     if (bytes[order[0]] > budget) throw std::runtime_error("not enough device memory for the multi-domain scratch of one region");
     std::vector<long long> slot_off(nmd);
     std::vector<int> batch_begin{0};
@@ -281,7 +281,8 @@ static void run_md(witch_ehmm *e, witch_queries *q, int nmd, cudaStream_t st_lis
         W.counter = e->mdcounter.p + 2 * b;
         int grid = (int)std::min<long long>((nb + MD_WARPS - 1) / MD_WARPS, (long long)e->num_sms * std::max(occ1, 1));
         WITCH_LAUNCH(md_forward_kernel, grid, MD_WARPS * 32, smem, st)(e->view(), q->view(), W);
-        WITCH_LAUNCH(md_trace_kernel, (nb + 127) / 128, 128, 0, st)(e->view(), q->view(), W);
+        if (e->Kp == 29) WITCH_LAUNCH(md_trace_kernel<20>, (nb + 127) / 128, 128, 0, st)(e->view(), q->view(), W);
+        else WITCH_LAUNCH(md_trace_kernel<4>, (nb + 127) / 128, 128, 0, st)(e->view(), q->view(), W);
         W.counter = e->mdcounter.p + 2 * b + 1;
         grid = (int)std::min<long long>((nb + MD_WARPS - 1) / MD_WARPS, (long long)e->num_sms * std::max(occ3, 1));
         WITCH_LAUNCH(md_cluster_kernel, grid, MD_WARPS * 32, 0, st)(e->view(), q->view(), W);

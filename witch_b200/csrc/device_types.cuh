@@ -33,6 +33,12 @@ struct DevEhmm {
     const long long *otoff;
     const long long *oroff;
     const int *oQ;
+    // the same values indexed by NODE for the trace walk of that branch (one 128-bit load per step instead of scattered
+    // scalars): ont8[onoff[h] + k] = {BM,MM,IM,DM into node k | MD,DD,MI,II of node k}, onem[(onoff[h] + k) * KE + x] =
+    // match odds of canonical residue x at node k (KE = 4 or 20)
+    const float *ont8;
+    const float *onem;
+    const long long *onoff;
     int H;
     int Kp;
 };

@@ -43,7 +43,7 @@ struct MdWork {
     MdOut *out;
 };
 
-struct MdLayout { long long hdr, dp, xmx, acc, sp, asg, epc, tkb, total; };
+struct MdLayout { long long hdr, dp, xmx, acc, sp, asg, epc, n2log, total; };
 // slot of one region of Lcap residues against a model of Mcap nodes (Qcap striped vectors per row)
 __host__ __device__ inline MdLayout md_layout(int Lcap, int Qcap, int Mcap, int nsp_cap) {
     MdLayout l;
@@ -55,7 +55,7 @@ __host__ __device__ inline MdLayout md_layout(int Lcap, int Qcap, int Mcap, int 
     l.sp = o; o += (long long)nsp_cap * 5 * 4;
     l.asg = o; o += (long long)nsp_cap * 4;
     l.epc = o; o += (long long)((Lcap > Mcap ? Lcap : Mcap) + 4) * 4;
-    l.tkb = o; o += (long long)(Lcap + 4) * 4;
+    l.n2log = o; o += (long long)nsp_cap * 20 * 4;   // null2 odds of every sampled domain (K <= 20 floats each)
     l.total = (o + 255) / 256 * 256;
     return l;
 }
@@ -70,8 +70,10 @@ __device__ __forceinline__ float md_add(float a, float b) { return __fadd_rn(a, 
 
 #ifdef WITCH_HOST_SIM
 static inline void md_prefetch(const void *) {}
+static inline void md_prefetch_l2(const void *) {}
 #else
 __device__ __forceinline__ void md_prefetch(const void *p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
+__device__ __forceinline__ void md_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 #endif
 
 __device__ __forceinline__ unsigned md_mix3(unsigned a, unsigned b, unsigned c) {
@@ -138,7 +140,8 @@ struct MdCtx {
     float pmove, ploop;
     size_t RW;
     float *dp, *xmx, *acc;
-    int *hdr, *spi, *spj, *spk, *spm, *spt, *asg, *epc, *tkb;
+    int *hdr, *spi, *spj, *spk, *spm, *spt, *asg, *epc;
+    float *n2log;
 };
 __device__ __forceinline__ MdCtx md_ctx(const DevEhmm &E, const DevQueries &Qs, const MdWork &W, int j) {
     MdCtx c;
@@ -162,7 +165,7 @@ __device__ __forceinline__ MdCtx md_ctx(const DevEhmm &E, const DevQueries &Qs, 
     c.spi = (int *)(slot + lay.sp); c.spj = c.spi + W.nsp_cap; c.spk = c.spj + W.nsp_cap; c.spm = c.spk + W.nsp_cap; c.spt = c.spm + W.nsp_cap;
     c.asg = (int *)(slot + lay.asg);
     c.epc = (int *)(slot + lay.epc);
-    c.tkb = (int *)(slot + lay.tkb);
+    c.n2log = (float *)(slot + lay.n2log);
     return c;
 }
 
@@ -322,145 +325,188 @@ __global__ void __launch_bounds__(MD_WARPS * 32) md_forward_kernel(DevEhmm E, De
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Kernel 2: the 200 stochastic traces of a region, its position-specific null2 and its sampled domains. The walk is
-// sequential by nature (one random-number stream per region), so ONE THREAD per region: the parallelism is across the
-// regions of the batch (ordered by size, so the lanes of a warp walk matrices of similar shape).
+// Kernel 2: the 200 stochastic traces of a region and its sampled domains. The walk is sequential by nature (one
+// random-number stream per region, every choice depends on the previous one), so ONE THREAD per region: the parallelism
+// is across the regions of the batch (ordered by size, so the lanes of a warp walk matrices of similar shape), and what
+// bounds a walk is the latency of one dependent memory access per step. The step is therefore written so that
+//  * the three cell states (M, D, I) share ONE branch-free body: cell / transition addresses are selected by state, all
+//    loads of a step are independent of each other (one memory latency per step whatever mix of states a warp holds),
+//    the choice among 4 or 2 paths is the same code with zero-padded paths;
+//  * the emission odds of a step (null2 sums) are loaded one step late, together with the next step's cell;
+//  * the cell the walk needs MD_PF steps later if it stays on the diagonal (M -> M, by far the most likely path) is
+//    prefetched into L2 every step;
+//  * N -> N steps (no random number, no effect) are skipped: reaching N ends the trace;
+//  * the choice of an E state's cell scans its row MD_ESCAN striped vectors per iteration (a state of its own), so a lane
+//    that scans does not hold up the lanes that walk.
+// Per sampled domain the kernel logs its coordinates and its null2 odds; the per-residue accumulation happens in the
+// clustering kernel.
+constexpr int MD_ESCAN = 2;   // striped vectors examined per E-scan iteration
+#ifndef WITCH_MD_PF
+#define WITCH_MD_PF 6
+#endif
+constexpr int MD_PF = WITCH_MD_PF;   // diagonal prefetch distance (steps)
+
+// esl_vec_FNorm + esl_rnd_FChoose for n = 2 or 4 paths (p2 = p3 = 0 when n = 2: adding an exact zero changes no rounding)
+__device__ __forceinline__ int md_choose4(unsigned &rng, float p0, float p1, float p2, float p3, int n) {
+    const float s = md_add(md_add(md_add(p0, p1), p2), p3);
+    if (s != 0.f) { p0 = p0 / s; p1 = p1 / s; p2 = p2 / s; p3 = p3 / s; }
+    else { const float u = 1.0f / (float)n; p0 = u; p1 = u; p2 = (n == 4) ? u : 0.f; p3 = p2; }
+    const double roll = md_rand(rng);
+    const double d0 = (double)p0, d1 = d0 + (double)p1, d2 = d1 + (double)p2, norm = d2 + (double)p3;
+    int c = n - 1;
+    if (n == 4 && d2 / norm > roll) c = 2;
+    if (d1 / norm > roll) c = 1;
+    if (d0 / norm > roll) c = 0;
+    return c;
+}
+
+template <int K>
 __global__ void __launch_bounds__(128) md_trace_kernel(DevEhmm E, DevQueries Qs, MdWork W) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= W.end - W.begin) return;
     const MdCtx cx = md_ctx(E, Qs, W, j);
-    const int Q = cx.Q, Lr = cx.Lr, K = cx.K;
-    const float *tfv = cx.tfv, *rfv = cx.rfv, *dp = cx.dp, *xmx = cx.xmx;
-    const uint8_t *rd = cx.rd;
+    const int Q = cx.Q, Lr = cx.Lr;
+    const float *__restrict__ dp = cx.dp, *__restrict__ xmx = cx.xmx;
+    const float *__restrict__ nt8 = E.ont8 + E.onoff[cx.R.h] * 8, *__restrict__ nem = E.onem + E.onoff[cx.R.h] * K;
     const float pmove = cx.pmove, ploop = cx.ploop;
     const size_t RW = cx.RW;
-    float *acc = cx.acc;
+    float *n2log = cx.n2log;
     const long long clk0 = clock64();
-    enum { tM = 1, tD = 2, tI = 3, tS = 4, tN = 5, tB = 6, tE = 7, tC = 8, tJ = 10 };
-    for (int p = 0; p <= Lr + 1; p++) acc[p] = 0.f;
+    enum { tM = 1, tD = 2, tI = 3, tS = 4, tN = 5, tB = 6, tE = 7, tC = 8, tJ = 10, tESCAN = 11 };
     unsigned rng = md_mix3(42u, 87654321u, 12345678u);
     if (rng == 0u) rng = 42u;
-    int nsp = 0, oflow = 0;
-    for (int t = 0; t < MD_NSAMPLES; t++) {
-        int i = Lr, k = 0, s0 = tC, ndom = 0, hi = Lr;
-        int sqto = 0, sqfrom = 0, hto = 0, hfrom = 0, Ld = 0;
-        int cq = 0, cr = 0;   // (k-1) % Q and (k-1) / Q of the current node, kept incrementally
-        double sums[20];      // sum over the running domain's emitting states of the match odds of every residue
-        while (s0 != tS) {
-            int s1;
-            const float *x1 = xmx + (size_t)i * 8, *x0 = xmx + (size_t)(i > 0 ? i - 1 : 0) * 8;
-            float path[4];
-            if (s0 == tM) {
-                k--;
-                const int q = cq, r = cr;   // = k % Q, k / Q of the decremented k
-                if (--cq < 0) { cq += Q; cr--; }
-                const float *tp = tfv + (size_t)q * 28 + r;
-                const float *pr = dp + (size_t)(i - 1) * RW;
-                float mp = 0.f, dd = 0.f, ip = 0.f;
-                if (q > 0) { const float *v = pr + (size_t)(q - 1) * 12 + r; mp = v[0]; dd = v[4]; ip = v[8]; }
-                else if (r > 0) { const float *v = pr + (size_t)(Q - 1) * 12 + r - 1; mp = v[0]; dd = v[4]; ip = v[8]; }
-                path[0] = md_mul(x0[3], tp[0]); path[1] = md_mul(mp, tp[4]); path[2] = md_mul(ip, tp[8]); path[3] = md_mul(dd, tp[12]);
-                const int c = md_choose(rng, path, 4);
-                s1 = (c == 0) ? tB : (c == 1) ? tM : (c == 2) ? tI : tD;
-                i--;
-            } else if (s0 == tD) {
-                k--;
-                const int q = cq, r = cr;
-                if (--cq < 0) { cq += Q; cr--; }
-                const float *crow = dp + (size_t)i * RW;
-                float mp = 0.f, dd = 0.f, tmd = 0.f, tdd = 0.f;
-                if (q > 0) {
-                    mp = crow[(size_t)(q - 1) * 12 + r]; dd = crow[(size_t)(q - 1) * 12 + 4 + r];
-                    tmd = tfv[(size_t)(q - 1) * 28 + 16 + r]; tdd = tfv[(size_t)Q * 28 + (size_t)(q - 1) * 4 + r];
-                } else if (r > 0) {
-                    mp = crow[(size_t)(Q - 1) * 12 + r - 1]; dd = crow[(size_t)(Q - 1) * 12 + 4 + r - 1];
-                    tmd = tfv[(size_t)(Q - 1) * 28 + 16 + r - 1]; tdd = tfv[(size_t)Q * 28 + (size_t)(Q - 1) * 4 + r - 1];
-                }
-                path[0] = md_mul(mp, tmd); path[1] = md_mul(dd, tdd);
-                s1 = md_choose(rng, path, 2) == 0 ? tM : tD;
-            } else if (s0 == tI) {
-                const int q = cq, r = cr;
-                const float *pr = dp + (size_t)(i - 1) * RW + (size_t)q * 12 + r;
-                path[0] = md_mul(pr[0], tfv[(size_t)q * 28 + 20 + r]);
-                path[1] = md_mul(pr[8], tfv[(size_t)q * 28 + 24 + r]);
-                s1 = md_choose(rng, path, 2) == 0 ? tM : tI;
-                i--;
-            } else if (s0 == tN) {
-                s1 = (i == 0) ? tS : tN;
-            } else if (s0 == tC) {
-                path[0] = md_mul(ploop, x0[4]);
-                path[1] = md_mul(md_mul(0.5f, x1[0]), x1[5]);
-                s1 = md_choose(rng, path, 2) == 0 ? tC : tE;
-            } else if (s0 == tJ) {
-                path[0] = md_mul(ploop, x0[2]);
-                path[1] = md_mul(md_mul(0.5f, x1[0]), x1[5]);
-                s1 = md_choose(rng, path, 2) == 0 ? tJ : tE;
-            } else if (s0 == tB) {
-                path[0] = md_mul(pmove, x1[1]);
-                path[1] = md_mul(pmove, x1[2]);
-                s1 = md_choose(rng, path, 2) == 0 ? tN : tJ;
-            } else {   // E: one roll against the running sum over all M/D cells of row i, in HMMER's striped order
-                const double roll = md_rand(rng);
-                const float norm = 1.0f / x1[0];
-                const float *row = dp + (size_t)i * RW;
-                double sum = 0.0;
-                int kk = 1;
-                s1 = tM;
-                bool found = false;
-                for (int q = 0; q < Q && !found; q++) {
-                    const float4 m4 = *reinterpret_cast<const float4 *>(row + (size_t)q * 12), d4 = *reinterpret_cast<const float4 *>(row + (size_t)q * 12 + 4);
-                    const float v8[8] = {m4.x, m4.y, m4.z, m4.w, d4.x, d4.y, d4.z, d4.w};
+    int nsp = 0, oflow = 0, t = 0;
+    int i = Lr, k = 0, s0 = tC, ndom = 0;
+    int sqto = 0, sqfrom = 0, hto = 0, hfrom = 0, Ld = 0;
+    int cq = 0, cr = 0;        // striped position of node k: (k-1) % Q, (k-1) / Q
+    int eq = 0;                // E scan: next striped vector
+    double eroll = 0.0, esum = 0.0;
+    float enorm = 0.f;
+    bool pend = false;         // an emitting step whose odds are not in sums[] yet
+    int pek = 0;               // its node
+    double sums[K];            // sum over the running domain's emitting states of the match odds of every residue
 #pragma unroll
-                    for (int r = 0; r < 8; r++) {
-                        sum += (double)md_mul(v8[r], norm);
-                        if (!found && sum > roll) { kk = (r & 3) * Q + q + 1; s1 = (r < 4) ? tM : tD; found = true; }
-                    }
-                }
-                k = kk;
-                cq = (kk - 1) % Q; cr = (kk - 1) / Q;
-                sqto = 0; sqfrom = 0; hto = 0; hfrom = 0; Ld = 0;   // a new domain starts (seen from its end)
-                for (int x = 0; x < K; x++) sums[x] = 0.0;
+    for (int x = 0; x < K; x++) sums[x] = 0.0;
+    for (;;) {
+        int s1;
+        if (s0 == tM || s0 == tD || s0 == tI) {
+            // ---- one step out of a cell state: every load below is independent of the others
+            const bool isM = s0 == tM, isD = s0 == tD, isI = s0 == tI;
+            int pq = cq - 1, pr = cr;                  // position of node k-1
+            if (pq < 0) { pq += Q; pr--; }
+            const bool hasprev = pr >= 0;
+            const int lq = isI ? cq : (hasprev ? pq : 0), lr = isI ? cr : (hasprev ? pr : 0);   // cell to look at
+            const int lrow = isD ? i : i - 1;
+            const float *cell = dp + (size_t)lrow * RW + (size_t)lq * 12 + lr;
+            // transitions: {BM,MM,IM,DM into k} for M, {MD,DD} of node k-1 for D, {MI,II} of node k for I -- one 128-bit load
+            const float4 T = __ldg(reinterpret_cast<const float4 *>(nt8 + (size_t)(isD ? (hasprev ? k - 1 : 0) : k) * 8 + (isM ? 0 : 4)));
+            float vM = cell[0], vD = cell[4], vI = cell[8];
+            const float xB = xmx[(size_t)(i - 1) * 8 + 3];
+            float em[K];
+#pragma unroll
+            for (int x = 0; x < K; x += 4) {
+                const float4 e4 = __ldg(reinterpret_cast<const float4 *>(nem + (size_t)pek * K + x));
+                em[x] = e4.x; em[x + 1] = e4.y; em[x + 2] = e4.z; em[x + 3] = e4.w;
             }
-            if (s1 == tM || s1 == tI) {   // (3.1b2 counts a residue emitted by I_k in the MATCH cell of node k)
-                if (s1 == tM) { if (sqto == 0) { sqto = i; hto = k; } sqfrom = i; hfrom = k; }
-                Ld++;
-                for (int x = 0; x < K; x++) sums[x] += (double)rfv[((size_t)x * Q + cq) * 4 + cr];
-            } else if (s1 == tB) {
-                // domain sqfrom..sqto complete: null2 odds of its states, accumulated per residue
-                float null2[20];
+            {   // the cell MD_PF steps down the diagonal
+                int fq = cq - 1 - MD_PF, fr = cr;
+                if (fq < 0) { fq += Q; fr--; }
+                if (fq < 0) { fq += Q; fr--; }
+                const int frow = i - 1 - MD_PF;
+                if (frow >= 0 && fr >= 0 && fq >= 0) md_prefetch(dp + (size_t)frow * RW + (size_t)fq * 12 + fr);
+            }
+            const float t0 = isI ? T.z : T.x, t1 = isI ? T.w : T.y, t2 = T.z, t3 = T.w;
+            if (!hasprev && !isI) { vM = 0.f; vD = 0.f; vI = 0.f; }
+            if (pend) {
+#pragma unroll
+                for (int x = 0; x < K; x++) sums[x] += (double)em[x];
+                pend = false;
+            }
+            const float p0 = md_mul(isM ? xB : vM, t0);   // (node 1 has no predecessor cell: those paths are exactly 0)
+            const float p1 = md_mul(isM ? vM : isD ? vD : vI, t1);
+            const float p2 = isM ? md_mul(vI, t2) : 0.f;
+            const float p3 = isM ? md_mul(vD, t3) : 0.f;
+            const int c = md_choose4(rng, p0, p1, p2, p3, isM ? 4 : 2);
+            // M: B M I D | D: M D | I: M I
+            s1 = isM ? ((c == 0) ? tB : (c == 1) ? tM : (c == 2) ? tI : tD) : (c == 0) ? tM : (isD ? tD : tI);
+            if (!isI) { k--; cq = pq; cr = pr; }
+            if (!isD) i--;
+        } else if (s0 == tESCAN) {
+            // one roll against the running sum over all M/D cells of row i, in HMMER's striped order
+            const float *row = dp + (size_t)i * RW;
+            bool found = false;
+            int kk = 1, ss = tM;
+            const int qe = min(eq + MD_ESCAN, Q);
+            if (qe + 4 * MD_ESCAN < Q) md_prefetch(row + (size_t)(qe + 4 * MD_ESCAN) * 12);   // a few iterations ahead
+#pragma unroll
+            for (int q = eq; q < qe; q++) {
+                const float4 m4 = *reinterpret_cast<const float4 *>(row + (size_t)q * 12), d4 = *reinterpret_cast<const float4 *>(row + (size_t)q * 12 + 4);
+                const float v8[8] = {m4.x, m4.y, m4.z, m4.w, d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+                for (int r = 0; r < 8; r++) {
+                    esum += (double)md_mul(v8[r], enorm);
+                    if (!found && esum > eroll) { kk = (r & 3) * Q + q + 1; ss = (r < 4) ? tM : tD; found = true; }
+                }
+            }
+            eq = qe;
+            if (!found && eq < Q) continue;   // still scanning
+            // (not found at all: the roll sits within rounding of 1; HMMER would wrap around -- first cell)
+            k = kk; s1 = ss;
+            cq = (kk - 1) % Q; cr = (kk - 1) / Q;
+        } else {
+            // ---- special states C, J, B (N never becomes the current state: reaching it ends the trace)
+            const bool isB = s0 == tB, isC = s0 == tC;
+            const float *x1 = xmx + (size_t)i * 8, *x0 = xmx + (size_t)(i > 0 ? i - 1 : 0) * 8;
+            const float a0 = isB ? x1[1] : isC ? x0[4] : x0[2];
+            const float b0 = x1[0], b2 = x1[2], b5 = x1[5];
+            const float p0 = md_mul(isB ? pmove : ploop, a0);
+            const float p1 = isB ? md_mul(pmove, b2) : md_mul(md_mul(0.5f, b0), b5);
+            const int c = md_choose4(rng, p0, p1, 0.f, 0.f, 2);
+            s1 = isB ? (c == 0 ? tN : tJ) : (c == 0 ? s0 : tE);
+            if (s1 == s0) i--;   // C -> C, J -> J
+        }
+        // ---- consequences of the step
+        if (s1 == tE) {   // a new domain starts (seen from its end): draw the roll, then scan row i over the next iterations
+            eroll = md_rand(rng);
+            enorm = 1.0f / xmx[(size_t)i * 8];
+            esum = 0.0; eq = 0;
+            sqto = 0; sqfrom = 0; hto = 0; hfrom = 0; Ld = 0;
+#pragma unroll
+            for (int x = 0; x < K; x++) sums[x] = 0.0;
+#pragma unroll
+            for (int z = 0; z < 4; z++) md_prefetch(dp + (size_t)i * RW + 32 * z);
+            s0 = tESCAN;
+            continue;
+        }
+        if (s1 == tM || s1 == tI) {   // (3.1b2 counts a residue emitted by I_k in the MATCH cell of node k)
+            if (s1 == tM) { if (sqto == 0) { sqto = i; hto = k; } sqfrom = i; hfrom = k; }
+            Ld++;
+            pend = true; pek = k;
+        } else if (s1 == tB) {
+            // domain sqfrom..sqto complete: log it with its null2 odds (accumulated per residue by the clustering kernel)
+            if (ndom < MD_MAXDOM && nsp + ndom < W.nsp_cap) {
+                const int z = nsp + ndom;
+                cx.spi[z] = sqfrom + cx.R.i0 - 1; cx.spj[z] = sqto + cx.R.i0 - 1; cx.spk[z] = hfrom; cx.spm[z] = hto; cx.spt[z] = t;
                 const float nrm = (float)(1.0 / (double)(float)Ld);
-                for (int x = 0; x < K; x++) null2[x] = (float)(sums[x] * (double)nrm);
-                for (int p = sqto + 1; p <= hi; p++) acc[p] = md_add(acc[p], 1.0f);
-                for (int p = sqfrom + 1; p <= sqto; p++) {
-                    const int code = Qs.symrow[rd[p - 1]];
-                    float v;
-                    if (code < K) v = null2[code];
-                    else {
-                        const unsigned mask = md_degen_mask(E.Kp, code);
-                        float sg = 0.f; int n = 0;
-                        for (int x = 0; x < K; x++) if (mask >> x & 1u) { sg += null2[x]; n++; }
-                        v = n ? sg / (float)n : 1.0f;
-                    }
-                    acc[p] = md_add(acc[p], v);
-                }
-                hi = sqfrom;   // (HMMER gives residue sqfrom the neutral 1.0 as well)
-                if (ndom < MD_MAXDOM && nsp + ndom < W.nsp_cap) {
-                    const int z = nsp + ndom;
-                    cx.spi[z] = sqfrom + cx.R.i0 - 1; cx.spj[z] = sqto + cx.R.i0 - 1; cx.spk[z] = hfrom; cx.spm[z] = hto; cx.spt[z] = t;
-                    ndom++;
-                } else oflow = 1;
+#pragma unroll
+                for (int x = 0; x < K; x++) n2log[(size_t)z * K + x] = (float)(sums[x] * (double)nrm);
+                ndom++;
+            } else oflow = 1;
+        }
+        s0 = s1;
+        if (s1 == tN) {
+            // end of trace t (N -> ... -> S consumes no random number): its domains enter the ensemble in sequence order
+            // (they were found last to first)
+            for (int a = nsp, b = nsp + ndom - 1; a < b; a++, b--) {
+                int tmp;
+                tmp = cx.spi[a]; cx.spi[a] = cx.spi[b]; cx.spi[b] = tmp; tmp = cx.spj[a]; cx.spj[a] = cx.spj[b]; cx.spj[b] = tmp;
+                tmp = cx.spk[a]; cx.spk[a] = cx.spk[b]; cx.spk[b] = tmp; tmp = cx.spm[a]; cx.spm[a] = cx.spm[b]; cx.spm[b] = tmp;
+                for (int x = 0; x < K; x++) { const float f = n2log[(size_t)a * K + x]; n2log[(size_t)a * K + x] = n2log[(size_t)b * K + x]; n2log[(size_t)b * K + x] = f; }
             }
-            if ((s1 == tN || s1 == tJ || s1 == tC) && s1 == s0) i--;
-            s0 = s1;
+            nsp += ndom;
+            if (++t >= MD_NSAMPLES) break;
+            i = Lr; k = 0; s0 = tC; ndom = 0; cq = 0; cr = 0;
         }
-        for (int p = 1; p <= hi; p++) acc[p] = md_add(acc[p], 1.0f);
-        // the trace's domains enter the ensemble in sequence order (they were found last to first): reverse the segment
-        for (int a = nsp, b = nsp + ndom - 1; a < b; a++, b--) {
-            int tmp;
-            tmp = cx.spi[a]; cx.spi[a] = cx.spi[b]; cx.spi[b] = tmp; tmp = cx.spj[a]; cx.spj[a] = cx.spj[b]; cx.spj[b] = tmp;
-            tmp = cx.spk[a]; cx.spk[a] = cx.spk[b]; cx.spk[b] = tmp; tmp = cx.spm[a]; cx.spm[a] = cx.spm[b]; cx.spm[b] = tmp;
-        }
-        nsp += ndom;
     }
     cx.hdr[0] = nsp; cx.hdr[1] = oflow; cx.hdr[3] = (int)((clock64() - clk0) >> 10);
 }
@@ -487,6 +533,35 @@ __global__ void __launch_bounds__(MD_WARPS * 32) md_cluster_kernel(DevEhmm E, De
         int oflow = cx.hdr[1];
         const long long clk1 = 0, clk0 = 0, clk2 = clock64();
         (void)clk1; (void)clk0;
+        // per-residue null2: every trace adds the odds of the domain that covers the residue (HMMER gives a domain's first
+        // residue the neutral 1.0 as well), or 1.0; float additions in trace order, as hmmsearch accumulates them
+        {
+            const int K = cx.K;
+            const float *n2log = cx.n2log;
+            for (int p = 1 + lane; p <= Lr; p += 32) {
+                const int pa = p + R.i0 - 1;   // absolute position
+                const int code = Qs.symrow[cx.rd[p - 1]];
+                const unsigned mask = code < K ? 0u : md_degen_mask(E.Kp, code);
+                float a = 0.f;
+                int d = 0;
+                for (int t = 0; t < MD_NSAMPLES; t++) {
+                    float v = 1.0f;
+                    for (; d < nsp && spt[d] == t; d++)
+                        if (spi[d] < pa && pa <= spj[d]) {
+                            const float *n2 = n2log + (size_t)d * K;
+                            if (code < K) v = n2[code];
+                            else {
+                                float sg = 0.f; int n = 0;
+                                for (int x = 0; x < K; x++) if (mask >> x & 1u) { sg += n2[x]; n++; }
+                                v = n ? sg / (float)n : 1.0f;
+                            }
+                        }
+                    a = md_add(a, v);
+                }
+                acc[p] = a;
+            }
+        }
+        __syncwarp();
         // ln of the mean null2 odds per residue -> acc[]; sum over the region
         float regc = 0.f;
         for (int p = 1 + lane; p <= Lr; p += 32) { const float v = logf(acc[p] / (float)MD_NSAMPLES); acc[p] = v; regc += v; }

@@ -103,9 +103,9 @@ struct witch_ehmm {
     std::vector<long long> poff, eoff;
     std::vector<int> hrank;   // launch order of the HMMs: longer models first (stable)
     int maxQ = 0;
-    DevBuf<float> tMM, tMI, tMD, tIM, tII, tDM, tDD, entry, gD, emis, otfv, orfv;
+    DevBuf<float> tMM, tMI, tMD, tIM, tII, tDM, tDD, entry, gD, emis, otfv, orfv, ont8, onem;
     DevBuf<int> dM, dstride, dnseq, doQ, dhrank;
-    DevBuf<long long> dpoff, deoff, dotoff, doroff;
+    DevBuf<long long> dpoff, deoff, dotoff, doroff, donoff;
     // reusable workspaces (owned by the handle: stage calls neither allocate nor free once they have grown)
     DevBuf<float> scratch, f1, f2;
     DevBuf<unsigned> counter;
@@ -140,6 +140,7 @@ struct witch_ehmm {
         v.tMM = tMM.p; v.tMI = tMI.p; v.tMD = tMD.p; v.tIM = tIM.p; v.tII = tII.p; v.tDM = tDM.p; v.tDD = tDD.p;
         v.entry = entry.p; v.gD = gD.p; v.emis = emis.p; v.M = dM.p; v.stride = dstride.p; v.poff = dpoff.p; v.eoff = deoff.p;
         v.otfv = otfv.p; v.orfv = orfv.p; v.otoff = dotoff.p; v.oroff = doroff.p; v.oQ = doQ.p;
+        v.ont8 = ont8.p; v.onem = onem.p; v.onoff = donoff.p;
         v.H = H; v.Kp = Kp;
         return v;
     }
@@ -224,16 +225,33 @@ extern "C" int witch_ehmm_create(int n_hmm, const char *const *paths, witch_ehmm
         e->dM.upload(e->M); e->dstride.upload(e->stride); e->dnseq.upload(e->nseq);
         e->dpoff.upload(e->poff); e->deoff.upload(e->eoff);
         {   // hmmsearch's striped float tables (multi-domain branch) and the launch rank of every HMM
-            std::vector<long long> otoff, oroff;
+            std::vector<long long> otoff, oroff, onoff;
             std::vector<int> oQ;
-            std::vector<float> tf, rf;
+            std::vector<float> tf, rf, nt8, nem;
+            const int KE = alphabet_info(e->alph).K;
             for (auto &p : ps) {
                 otoff.push_back((long long)tf.size()); oroff.push_back((long long)rf.size()); oQ.push_back(p.Q);
                 tf.insert(tf.end(), p.otfv.begin(), p.otfv.end());
                 rf.insert(rf.end(), p.orfv.begin(), p.orfv.end());
                 e->maxQ = std::max(e->maxQ, p.Q);
+                // node-indexed copies for the trace walk: node k sits at striped position q = (k-1) % Q, z = (k-1) / Q
+                const long long n0 = (long long)nt8.size() / 8;
+                onoff.push_back(n0);
+                const int Q = p.Q, NN = 4 * Q + 1;
+                nt8.resize((size_t)(n0 + NN) * 8, 0.f);
+                nem.resize((size_t)(n0 + NN) * KE, 0.f);
+                for (int k = 1; k < NN; k++) {
+                    const int q = (k - 1) % Q, z = (k - 1) / Q;
+                    float *t8 = &nt8[(size_t)(n0 + k) * 8];
+                    for (int tt = 0; tt < 4; tt++) t8[tt] = p.otfv[((size_t)7 * q + tt) * 4 + z];          // BM MM IM DM
+                    t8[4] = p.otfv[((size_t)7 * q + 4) * 4 + z];                                           // MD
+                    t8[5] = p.otfv[((size_t)7 * Q + q) * 4 + z];                                           // DD
+                    t8[6] = p.otfv[((size_t)7 * q + 5) * 4 + z]; t8[7] = p.otfv[((size_t)7 * q + 6) * 4 + z];   // MI II
+                    for (int x = 0; x < KE; x++) nem[(size_t)(n0 + k) * KE + x] = p.orfv[((size_t)x * Q + q) * 4 + z];
+                }
             }
             e->otfv.upload(tf); e->orfv.upload(rf); e->dotoff.upload(otoff); e->doroff.upload(oroff); e->doQ.upload(oQ);
+            e->ont8.upload(nt8); e->onem.upload(nem); e->donoff.upload(onoff);
             std::vector<int> horder(e->H);
             e->hrank.assign(e->H, 0);
             std::iota(horder.begin(), horder.end(), 0);
