@@ -54,6 +54,16 @@ int witch_device_count(void);
  * All profiles must share one alphabet. NSEQ (reference gcmm/loader.py:40-58, HMMSubset.num_taxa) is kept.
  */
 int witch_ehmm_create(int n_hmm, const char *const *hmm_paths, witch_ehmm **out);
+/*
+ * Same, through a serialised profile cache kept next to the HMM text (the reference re-reads and
+ * re-configures the hmmbuild.model.* files of an existing tree_decomp directory on every `-p` run,
+ * witch_msa/gcmm/loader.py:17-58 + the hmmsearch/hmmalign start-up of every job). cache_path: one binary file holding
+ * the configured profiles and the size + modification time of every source file; when it is present and every source
+ * file is unchanged the text is not parsed (*cache_hit = 1), otherwise the profiles are parsed and the file is
+ * (re)written atomically (*cache_hit = 0; an unwritable path is not an error). cache_hit may be NULL.
+ */
+int witch_ehmm_create_cached(int n_hmm, const char *const *hmm_paths, const char *cache_path, int *cache_hit,
+                             witch_ehmm **out);
 void witch_ehmm_destroy(witch_ehmm *e);
 int witch_ehmm_count(const witch_ehmm *e);
 int witch_ehmm_alphabet(const witch_ehmm *e);

@@ -61,6 +61,39 @@ def test_no_cpu_fallback_without_gpu(lib, tmp_path):
         wb.EHMM(paths)
 
 
+def test_profile_cache_is_written_validated_and_invalidated(lib, tmp_path):
+    """witch_ehmm_create_cached: the serialised profiles are written next to the HMM text on the first call and
+    accepted on the next one only while every source file is unchanged. (Without a GPU the call itself still ends in
+    'no CUDA device' -- the cache is host-side work that happens before the upload.)"""
+    import ctypes
+    import torch
+    from golden_util import load_set
+    _, _, paths = load_set("amino_small", str(tmp_path))
+    cache = str(tmp_path / "witch_b200.profiles")
+    arr = (ctypes.c_char_p * len(paths))(*[p.encode() for p in paths])
+
+    def call():
+        h, hit = ctypes.c_void_p(), ctypes.c_int(-1)
+        rc = lib.witch_ehmm_create_cached(len(paths), arr, cache.encode(), ctypes.byref(hit), ctypes.byref(h))
+        if rc == 0:
+            lib.witch_ehmm_destroy(h)
+        else:
+            assert not torch.cuda.is_available() and b"no CUDA device" in lib.witch_last_error()
+        return hit.value
+
+    assert call() == 0 and os.path.getsize(cache) > 1000
+    assert call() == 1
+    st = os.stat(paths[0])
+    os.utime(paths[0], ns=(st.st_atime_ns, st.st_mtime_ns + 1_000_000_000))   # a source file changed: parse again, rewrite
+    assert call() == 0
+    assert call() == 1
+    with open(cache, "r+b") as f:   # a truncated / foreign file is ignored, never trusted
+        f.truncate(200)
+    assert call() == 0
+    assert call() == 1
+    assert lib.witch_ehmm_create_cached(len(paths), arr, None, None, ctypes.byref(ctypes.c_void_p())) == -1
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "witch_b200")
     for dp, _, files in os.walk(pkg):

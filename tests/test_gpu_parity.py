@@ -99,6 +99,26 @@ def test_scores_weights_columns_vs_oracle_and_golden(wb, setname, tmp_path):
     assert nbad <= nres // 2000, (setname, nbad, nres)
 
 
+def test_profile_cache_gives_identical_results(wb, tmp_path):
+    """An eHMM created from the serialised profile cache scores and aligns exactly like one parsed from the HMM text."""
+    gold, queries, paths = load_set("dna_sub8", str(tmp_path))
+    cache = str(tmp_path / "witch_b200.profiles")
+    E0 = wb.EHMM(paths)
+    E1 = wb.EHMM(paths, cache=cache)
+    E2 = wb.EHMM(paths, cache=cache)
+    assert not E1.cache_hit and E2.cache_hit
+    assert list(E2.M) == list(E0.M) and list(E2.nseq) == list(E0.nseq)
+    seqs = [s for _, s in queries[:40]]
+    a = wb.score(E0, wb.Queries(E0, seqs))
+    b = wb.score(E2, wb.Queries(E2, seqs))
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y, equal_nan=True)
+    pq = [qi for qi in range(len(seqs)) if a[1][qi, 0]][:10]
+    ca = wb.align(E0, wb.Queries(E0, seqs), pq, [0] * len(pq))
+    cb = wb.align(E2, wb.Queries(E2, seqs), pq, [0] * len(pq))
+    assert all(np.array_equal(x, y) for x, y in zip(ca, cb))
+
+
 def test_edge_cases(wb, tmp_path):
     gold, queries, paths = load_set("dna_small", str(tmp_path))
     E = wb.EHMM(paths)
@@ -174,13 +194,13 @@ def test_mirror_interface_end_to_end(wb, tmp_path):
     from witch_b200.gcmm import BatchedSearch
     gold, queries, paths = load_set("dna_small", str(tmp_path))
     rt = str(tmp_path / "runtime_breakdown.txt")
-    bs = BatchedSearch(paths, num_hmms=10, runtime_path=rt)
+    bs = BatchedSearch(paths, num_hmms=10, runtime_path=rt, profile_cache=str(tmp_path / "witch_b200.profiles"))
     bs.search([n for n, _ in queries], [s for _, s in queries])
     ranked = bs.rankBitscores()
     t2w = bs.writeWeights()
     bb = bs.getBackbones(t2w)
     lines = open(rt).read().splitlines()   # the reference's runtime_breakdown.txt format: "(tag) Time to ... (s): x"
-    assert [ln.split(")")[0] for ln in lines] == ["(gpu_score", "(gpu_weights", "(gpu_align"]
+    assert [ln.split(")")[0] for ln in lines] == ["(gpu_load", "(gpu_score", "(gpu_weights", "(gpu_align"]
     assert all(" (s): " in ln and float(ln.rsplit(": ", 1)[1]) >= 0 for ln in lines)
     names = [n for n, _ in queries]
     for h, hg in enumerate(gold["hmms"]):

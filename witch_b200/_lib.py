@@ -18,6 +18,8 @@ SYMBOLS = {
     "witch_version": (ctypes.c_char_p, []),
     "witch_device_count": (ctypes.c_int, []),
     "witch_ehmm_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_void_p)]),
+    "witch_ehmm_create_cached": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.c_char_p, ctypes.POINTER(ctypes.c_int),
+                                                ctypes.POINTER(ctypes.c_void_p)]),
     "witch_ehmm_destroy": (None, [ctypes.c_void_p]),
     "witch_ehmm_count": (ctypes.c_int, [ctypes.c_void_p]),
     "witch_ehmm_alphabet": (ctypes.c_int, [ctypes.c_void_p]),

@@ -19,12 +19,20 @@ class EHMM:
     """Ensemble of HMMER3 profiles on the current CUDA device (reference: the hmmbuild.model.* files of
     witch_msa/gcmm/algorithm.py:463-470 and HMMSubset of gcmm/loader.py:17-58)."""
 
-    def __init__(self, hmm_paths):
+    def __init__(self, hmm_paths, cache=None):
+        """cache: optional path of the serialised profile cache (e.g. <tree_decomp>/witch_b200.profiles): when it exists
+        and no HMM file changed since it was written the text is not parsed again (`self.cache_hit`)."""
         lib = _lib.load()
         self.paths = [str(p) for p in hmm_paths]
         arr = (ctypes.c_char_p * len(self.paths))(*[p.encode() for p in self.paths])
         h = ctypes.c_void_p()
-        check(lib.witch_ehmm_create(len(self.paths), arr, ctypes.byref(h)))
+        self.cache_hit = False
+        if cache is None:
+            check(lib.witch_ehmm_create(len(self.paths), arr, ctypes.byref(h)))
+        else:
+            hit = ctypes.c_int(0)
+            check(lib.witch_ehmm_create_cached(len(self.paths), arr, str(cache).encode(), ctypes.byref(hit), ctypes.byref(h)))
+            self.cache_hit = bool(hit.value)
         self._h = h
         self.n = lib.witch_ehmm_count(h)
         self.M = np.zeros(self.n, dtype=np.int32)

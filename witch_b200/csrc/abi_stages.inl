@@ -246,8 +246,13 @@ static void run_md(witch_ehmm *e, witch_queries *q, int nmd, cudaStream_t st_lis
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return bytes[a] > bytes[b]; });
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-    const long long budget = (long long)std::min<double>(110.0e9, 0.6 * (double)(free_b + e->mdbytes.n));
-    if (bytes[order[0]] > budget) throw std::runtime_error("not enough device memory for the multi-domain scratch of one region");
+    const long long budget_all = (long long)std::min<double>(110.0e9, 0.6 * (double)(free_b + e->mdbytes.n));
+    if (bytes[order[0]] > budget_all) throw std::runtime_error("not enough device memory for the multi-domain scratch of one region");
+    long long total_bytes = 0;
+    for (int r = 0; r < nmd; r++) total_bytes += bytes[r];
+    // a list that does not fit one batch is processed by two lanes (streams) on the two halves of the scratch
+    const int nlanes = (total_bytes > budget_all && 2 * bytes[order[0]] <= budget_all) ? 2 : 1;
+    const long long budget = (budget_all / nlanes) & ~255LL;
     std::vector<long long> slot_off(nmd);
     std::vector<int> batch_begin{0};
     long long used = 0, need = 0;
@@ -260,8 +265,9 @@ static void run_md(witch_ehmm *e, witch_queries *q, int nmd, cudaStream_t st_lis
     }
     batch_begin.push_back(nmd);
     const int nbatch = (int)batch_begin.size() - 1;
+    if (nlanes == 2) need = budget * 2;
     if ((size_t)need > e->mdbytes.n) { CUDA_TRY(cudaDeviceSynchronize()); e->mdbytes.alloc((size_t)need); }
-    if ((size_t)nmd > e->mdorder.n || (size_t)2 * nbatch + 2 > e->mdcounter.n) CUDA_TRY(cudaStreamSynchronize(st));
+    if ((size_t)nmd > e->mdorder.n || (size_t)2 * nbatch + 2 > e->mdcounter.n) { CUDA_TRY(cudaStreamSynchronize(st)); CUDA_TRY(cudaStreamSynchronize(e->aux2)); }
     e->mdorder.upload(order, st);
     e->mdslot.upload(slot_off, st);
     e->mdcounter.alloc((size_t)2 * nbatch + 2);
@@ -273,21 +279,39 @@ static void run_md(witch_ehmm *e, witch_queries *q, int nmd, cudaStream_t st_lis
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, md_forward_kernel, MD_WARPS * 32, smem));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, md_cluster_kernel, MD_WARPS * 32, 0));
     ScopedTimer tm(3, st, 0.0);
+    if (nlanes == 2) {   // the second lane starts once the lists are uploaded
+        CUDA_TRY(cudaEventRecord(e->ev_md, st));
+        CUDA_TRY(cudaStreamWaitEvent(e->aux2, e->ev_md, 0));
+    }
     for (int b = 0; b < nbatch; b++) {
+        cudaStream_t sb = (nlanes == 2 && (b & 1)) ? e->aux2 : st;
         MdWork W;
         W.regions = e->mdregs.p; W.order = e->mdorder.p; W.slot_off = e->mdslot.p; W.begin = batch_begin[b]; W.end = batch_begin[b + 1];
-        W.scratch = (char *)e->mdbytes.p; W.Qcap = Qcap; W.nsp_cap = nsp_cap; W.out = e->mdout.p;
+        W.scratch = (char *)e->mdbytes.p + ((nlanes == 2 && (b & 1)) ? budget : 0); W.Qcap = Qcap; W.nsp_cap = nsp_cap; W.out = e->mdout.p; W.spread = 1;
         const int nb = W.end - W.begin;
         W.counter = e->mdcounter.p + 2 * b;
         int grid = (int)std::min<long long>((nb + MD_WARPS - 1) / MD_WARPS, (long long)e->num_sms * std::max(occ1, 1));
-        WITCH_LAUNCH(md_forward_kernel, grid, MD_WARPS * 32, smem, st)(e->view(), q->view(), W);
-        if (e->Kp == 29) WITCH_LAUNCH(md_trace_kernel<20>, (nb + 127) / 128, 128, 0, st)(e->view(), q->view(), W);
-        else WITCH_LAUNCH(md_trace_kernel<4>, (nb + 127) / 128, 128, 0, st)(e->view(), q->view(), W);
+        WITCH_LAUNCH(md_forward_kernel, grid, MD_WARPS * 32, smem, sb)(e->view(), q->view(), W);
+        {   // walkers per warp: as few as the batch size allows while the GPU still holds every walker at once
+            static const int forced = [] { const char *s = getenv("WITCH_MD_SPREAD"); return s ? atoi(s) : 0; }();
+            const long long cap = (long long)e->num_sms * 512;   // (measured: c4-sized batches want 32 walkers per warp, a c2 slab's 155 regions one each)
+            int spread = 32;
+            while (spread > 1 && (long long)nb * spread > cap) spread >>= 1;
+            if (forced >= 1 && forced <= 32 && (forced & (forced - 1)) == 0) spread = forced;
+            W.spread = spread;
+            const unsigned tg = (unsigned)(((long long)nb * spread + 127) / 128);
+            if (e->Kp == 29) WITCH_LAUNCH(md_trace_kernel<20>, tg, 128, 0, sb)(e->view(), q->view(), W);
+            else WITCH_LAUNCH(md_trace_kernel<4>, tg, 128, 0, sb)(e->view(), q->view(), W);
+        }
         W.counter = e->mdcounter.p + 2 * b + 1;
         grid = (int)std::min<long long>((nb + MD_WARPS - 1) / MD_WARPS, (long long)e->num_sms * std::max(occ3, 1));
-        WITCH_LAUNCH(md_cluster_kernel, grid, MD_WARPS * 32, 0, st)(e->view(), q->view(), W);
+        WITCH_LAUNCH(md_cluster_kernel, grid, MD_WARPS * 32, 0, sb)(e->view(), q->view(), W);
         g_launches += 3;
         CUDA_TRY(cudaGetLastError());
+    }
+    if (nlanes == 2) {   // join the second lane
+        CUDA_TRY(cudaEventRecord(e->ev_md2, e->aux2));
+        CUDA_TRY(cudaStreamWaitEvent(st, e->ev_md2, 0));
     }
 }
 

@@ -3,6 +3,10 @@
 // reference's HMMER 3.1b2 binaries do with the file written at witch_msa/gcmm/algorithm.py:463-470.
 #include "hmm_profile.h"
 
+#include <sys/stat.h>
+#include <unistd.h>
+#include <cstdio>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -251,6 +255,85 @@ HostProfile load_profile(const std::string &path, int /*pad_to*/) {
     }
     build_striped(p, A, raw_t, raw_mat);
     return p;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// profile cache
+namespace {
+const char CACHE_MAGIC[8] = {'W', 'B', '2', 'E', 'H', 'M', 'M', '2'};
+struct SrcStamp { long long size, mtime_ns; };
+bool stamp_of(const std::string &path, SrcStamp &st) {
+    struct stat sb;
+    if (stat(path.c_str(), &sb) != 0) return false;
+    st.size = (long long)sb.st_size;
+    st.mtime_ns = (long long)sb.st_mtim.tv_sec * 1000000000LL + (long long)sb.st_mtim.tv_nsec;
+    return true;
+}
+template <typename T> bool wr(FILE *f, const T &v) { return fwrite(&v, sizeof(T), 1, f) == 1; }
+template <typename T> bool rd(FILE *f, T &v) { return fread(&v, sizeof(T), 1, f) == 1; }
+bool wr_vec(FILE *f, const std::vector<float> &v) {
+    const unsigned long long n = v.size();
+    return wr(f, n) && (n == 0 || fwrite(v.data(), sizeof(float), n, f) == n);
+}
+bool rd_vec(FILE *f, std::vector<float> &v, unsigned long long max_n) {
+    unsigned long long n = 0;
+    if (!rd(f, n) || n > max_n) return false;
+    v.resize(n);
+    return n == 0 || fread(v.data(), sizeof(float), n, f) == n;
+}
+std::vector<float> HostProfile::*const CACHE_FIELDS[] = {&HostProfile::tMM, &HostProfile::tMI, &HostProfile::tMD, &HostProfile::tIM,
+                                                        &HostProfile::tII, &HostProfile::tDM, &HostProfile::tDD, &HostProfile::entry,
+                                                        &HostProfile::gD, &HostProfile::emis, &HostProfile::otfv, &HostProfile::orfv};
+}  // namespace
+
+bool save_profile_cache(const std::string &cache_path, const std::vector<std::string> &hmm_paths, const std::vector<HostProfile> &ps) {
+    if (hmm_paths.size() != ps.size() || ps.empty()) return false;
+    const std::string tmp = cache_path + ".tmp." + std::to_string((long long)getpid());
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (!f) return false;
+    bool ok = fwrite(CACHE_MAGIC, 1, 8, f) == 8;
+    const int n = (int)ps.size();
+    ok = ok && wr(f, n);
+    for (int h = 0; ok && h < n; h++) {
+        SrcStamp st;
+        ok = stamp_of(hmm_paths[h], st) && wr(f, st.size) && wr(f, st.mtime_ns);
+        const HostProfile &p = ps[h];
+        ok = ok && wr(f, p.M) && wr(f, p.nseq) && wr(f, p.alph) && wr(f, p.stride) && wr(f, p.Q);
+        for (auto fld : CACHE_FIELDS) ok = ok && wr_vec(f, p.*fld);
+    }
+    ok = (fclose(f) == 0) && ok;
+    if (ok) ok = rename(tmp.c_str(), cache_path.c_str()) == 0;
+    if (!ok) remove(tmp.c_str());
+    return ok;
+}
+
+bool load_profile_cache(const std::string &cache_path, const std::vector<std::string> &hmm_paths, std::vector<HostProfile> &out) {
+    out.clear();
+    FILE *f = fopen(cache_path.c_str(), "rb");
+    if (!f) return false;
+    char magic[8];
+    int n = 0;
+    bool ok = fread(magic, 1, 8, f) == 8 && std::memcmp(magic, CACHE_MAGIC, 8) == 0 && rd(f, n) && n == (int)hmm_paths.size();
+    std::vector<HostProfile> ps;
+    for (int h = 0; ok && h < n; h++) {
+        SrcStamp now, was;
+        ok = stamp_of(hmm_paths[h], now) && rd(f, was.size) && rd(f, was.mtime_ns) && now.size == was.size && now.mtime_ns == was.mtime_ns;
+        HostProfile p;
+        ok = ok && rd(f, p.M) && rd(f, p.nseq) && rd(f, p.alph) && rd(f, p.stride) && rd(f, p.Q);
+        ok = ok && p.M > 0 && p.M <= (1 << 20) && p.stride > p.M && p.Q >= 2 && p.alph >= 0 && p.alph <= 2;
+        for (auto fld : CACHE_FIELDS) ok = ok && rd_vec(f, p.*fld, 64ull * (unsigned long long)(p.stride > 0 ? p.stride : 1));
+        if (ok) {
+            const int Kp = alphabet_info(p.alph).Kp;
+            ok = p.tMM.size() == (size_t)p.stride && p.tDD.size() == (size_t)p.stride && p.entry.size() == (size_t)p.stride &&
+                 p.gD.size() == (size_t)p.stride && p.emis.size() == (size_t)Kp * p.stride && p.otfv.size() == (size_t)32 * p.Q &&
+                 p.orfv.size() == (size_t)Kp * p.Q * 4;
+        }
+        if (ok) ps.push_back(std::move(p));
+    }
+    fclose(f);
+    if (!ok) return false;
+    out = std::move(ps);
+    return true;
 }
 
 }  // namespace witch

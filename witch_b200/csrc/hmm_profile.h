@@ -43,4 +43,12 @@ struct HostProfile {
 // Parse + configure. Throws std::runtime_error with a message on malformed input.
 HostProfile load_profile(const std::string &path, int pad_to);
 
+// Serialised configured profiles next to the HMM text ("profile cache", SURVEY.md 8f-3: a `-p` re-run of the reference
+// re-reads the same hmmbuild.model.* files, gcmm/loader.py:17-58): one binary file holding every array of every
+// HostProfile plus the size and modification time of each source file. load_profile_cache returns false (and leaves
+// `out` empty) when the file is missing, malformed, from another version, or any source file changed.
+bool load_profile_cache(const std::string &cache_path, const std::vector<std::string> &hmm_paths, std::vector<HostProfile> &out);
+// Atomic (temporary file + rename); returns false when the file cannot be written (the caller carries on without it).
+bool save_profile_cache(const std::string &cache_path, const std::vector<std::string> &hmm_paths, const std::vector<HostProfile> &ps);
+
 }  // namespace witch

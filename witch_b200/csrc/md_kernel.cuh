@@ -40,10 +40,13 @@ struct MdWork {
     unsigned *counter;
     char *scratch;
     int Qcap, nsp_cap;
+    int spread;            // trace kernel: one walker every `spread` threads (32 = one region per warp, 1 = one per thread)
     MdOut *out;
 };
 
-struct MdLayout { long long hdr, dp, xmx, acc, sp, asg, epc, n2log, total; };
+constexpr int MD_EBLK = 8;        // striped vectors per block of the two-level E scan
+__host__ __device__ inline int md_nblocks(int Q) { return (Q + MD_EBLK - 1) / MD_EBLK; }
+struct MdLayout { long long hdr, dp, xmx, acc, sp, asg, epc, n2log, bsum, total; };
 // slot of one region of Lcap residues against a model of Mcap nodes (Qcap striped vectors per row)
 __host__ __device__ inline MdLayout md_layout(int Lcap, int Qcap, int Mcap, int nsp_cap) {
     MdLayout l;
@@ -56,6 +59,8 @@ __host__ __device__ inline MdLayout md_layout(int Lcap, int Qcap, int Mcap, int 
     l.asg = o; o += (long long)nsp_cap * 4;
     l.epc = o; o += (long long)((Lcap > Mcap ? Lcap : Mcap) + 4) * 4;
     l.n2log = o; o += (long long)nsp_cap * 20 * 4;   // null2 odds of every sampled domain (K <= 20 floats each)
+    o = (o + 7) / 8 * 8;
+    l.bsum = o; o += (long long)(Lcap + 1) * md_nblocks(Qcap) * 8;   // per row: E-scan mass of every block of MD_EBLK striped vectors (double)
     l.total = (o + 255) / 256 * 256;
     return l;
 }
@@ -142,6 +147,7 @@ struct MdCtx {
     float *dp, *xmx, *acc;
     int *hdr, *spi, *spj, *spk, *spm, *spt, *asg, *epc;
     float *n2log;
+    double *bsum;
 };
 __device__ __forceinline__ MdCtx md_ctx(const DevEhmm &E, const DevQueries &Qs, const MdWork &W, int j) {
     MdCtx c;
@@ -166,6 +172,7 @@ __device__ __forceinline__ MdCtx md_ctx(const DevEhmm &E, const DevQueries &Qs, 
     c.asg = (int *)(slot + lay.asg);
     c.epc = (int *)(slot + lay.epc);
     c.n2log = (float *)(slot + lay.n2log);
+    c.bsum = (double *)(slot + lay.bsum);
     return c;
 }
 
@@ -316,6 +323,25 @@ __global__ void __launch_bounds__(MD_WARPS * 32) md_forward_kernel(DevEhmm E, De
                 float *x = xmx + (size_t)i * 8;
                 x[0] = fE; x[1] = fN; x[2] = fJ; x[3] = fB; x[4] = fC; x[5] = scale;
             }
+            {   // E-scan mass of every block of MD_EBLK vectors of the stored row (what a trace's choice of the E state's
+                // cell adds up: (double)(cell * 1/E), M cells then D cells of each vector), for the two-level scan
+                const float enorm = 1.0f / fE;
+                const int nblk = md_nblocks(Q);
+                double *bs = cx.bsum + (size_t)i * nblk;
+                for (int b = lane; b < nblk; b += 32) {
+                    double sum = 0.0;
+                    const int q1 = min(Q, (b + 1) * MD_EBLK);
+                    for (int q = b * MD_EBLK; q < q1; q++) {
+#pragma unroll
+                        for (int r = 0; r < 8; r++) {
+                            float v = (r < 4) ? sMv[q * 4 + r] : sDv[q * 4 + r - 4];
+                            if (resc) v = md_mul(v, inv);
+                            sum += (double)md_mul(v, enorm);
+                        }
+                    }
+                    bs[b] = sum;
+                }
+            }
             __syncwarp();
         }
 
@@ -340,7 +366,7 @@ __global__ void __launch_bounds__(MD_WARPS * 32) md_forward_kernel(DevEhmm E, De
 //    that scans does not hold up the lanes that walk.
 // Per sampled domain the kernel logs its coordinates and its null2 odds; the per-residue accumulation happens in the
 // clustering kernel.
-constexpr int MD_ESCAN = 2;   // striped vectors examined per E-scan iteration
+constexpr int MD_ESCAN = 4;   // striped vectors examined per iteration of the E scan's second level
 #ifndef WITCH_MD_PF
 #define WITCH_MD_PF 6
 #endif
@@ -362,8 +388,11 @@ __device__ __forceinline__ int md_choose4(unsigned &rng, float p0, float p1, flo
 
 template <int K>
 __global__ void __launch_bounds__(128) md_trace_kernel(DevEhmm E, DevQueries Qs, MdWork W) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= W.end - W.begin) return;
+    // A batch of few regions gives every walker a warp of its own (no serialisation of the three step bodies across
+    // regions, a private L1 footprint); a batch of many regions packs up to 32 walkers into a warp.
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = gt / W.spread;
+    if (gt % W.spread != 0 || j >= W.end - W.begin) return;
     const MdCtx cx = md_ctx(E, Qs, W, j);
     const int Q = cx.Q, Lr = cx.Lr;
     const float *__restrict__ dp = cx.dp, *__restrict__ xmx = cx.xmx;
@@ -372,7 +401,7 @@ __global__ void __launch_bounds__(128) md_trace_kernel(DevEhmm E, DevQueries Qs,
     const size_t RW = cx.RW;
     float *n2log = cx.n2log;
     const long long clk0 = clock64();
-    enum { tM = 1, tD = 2, tI = 3, tS = 4, tN = 5, tB = 6, tE = 7, tC = 8, tJ = 10, tESCAN = 11 };
+    enum { tM = 1, tD = 2, tI = 3, tS = 4, tN = 5, tB = 6, tE = 7, tC = 8, tJ = 10, tESCAN = 11, tEBLK = 12 };
     unsigned rng = md_mix3(42u, 87654321u, 12345678u);
     if (rng == 0u) rng = 42u;
     int nsp = 0, oflow = 0, t = 0;
@@ -431,13 +460,39 @@ __global__ void __launch_bounds__(128) md_trace_kernel(DevEhmm E, DevQueries Qs,
             s1 = isM ? ((c == 0) ? tB : (c == 1) ? tM : (c == 2) ? tI : tD) : (c == 0) ? tM : (isD ? tD : tI);
             if (!isI) { k--; cq = pq; cr = pr; }
             if (!isD) i--;
+        } else if (s0 == tEBLK) {
+            // E state, level 1: which block of MD_EBLK vectors holds the roll (running sum of the blocks' masses)
+            const int nblk = md_nblocks(Q);
+            const double *bs = cx.bsum + (size_t)i * nblk;
+            const int b1 = min(eq + 16, nblk);
+            double m16[16];
+#pragma unroll
+            for (int z = 0; z < 16; z++) m16[z] = (eq + z < b1) ? bs[eq + z] : 0.0;
+            bool hit = false;
+#pragma unroll
+            for (int z = 0; z < 16; z++) {
+                if (!hit && eq + z < b1) {
+                    if (esum + m16[z] > eroll) hit = true; else { esum += m16[z]; }
+                    if (hit) eq += z;
+                }
+            }
+            if (!hit) {
+                eq = b1;
+                if (eq < nblk) continue;
+                eq = Q; s0 = tESCAN;   // (the roll lies beyond the row's whole mass, i.e. within rounding of 1: level 2 resolves it)
+                continue;
+            }
+            eq *= MD_EBLK;          // first vector of the block; esum = mass of everything before it
+            s0 = tESCAN;
+            continue;
         } else if (s0 == tESCAN) {
-            // one roll against the running sum over all M/D cells of row i, in HMMER's striped order
+            // E state, level 2: one roll against the running sum over the M/D cells of row i from vector eq on, in HMMER's
+            // striped order (the running sum differs from HMMER's strictly sequential one by the association of the
+            // block masses: a choice can differ only when the roll lies within ~1e-13 of a cumulative probability)
             const float *row = dp + (size_t)i * RW;
             bool found = false;
             int kk = 1, ss = tM;
             const int qe = min(eq + MD_ESCAN, Q);
-            if (qe + 4 * MD_ESCAN < Q) md_prefetch(row + (size_t)(qe + 4 * MD_ESCAN) * 12);   // a few iterations ahead
 #pragma unroll
             for (int q = eq; q < qe; q++) {
                 const float4 m4 = *reinterpret_cast<const float4 *>(row + (size_t)q * 12), d4 = *reinterpret_cast<const float4 *>(row + (size_t)q * 12 + 4);
@@ -449,7 +504,7 @@ __global__ void __launch_bounds__(128) md_trace_kernel(DevEhmm E, DevQueries Qs,
                 }
             }
             eq = qe;
-            if (!found && eq < Q) continue;   // still scanning
+            if (!found && eq < Q) continue;   // (rounding at a block boundary: carry on into the next block)
             // (not found at all: the roll sits within rounding of 1; HMMER would wrap around -- first cell)
             k = kk; s1 = ss;
             cq = (kk - 1) % Q; cr = (kk - 1) / Q;
@@ -473,9 +528,7 @@ __global__ void __launch_bounds__(128) md_trace_kernel(DevEhmm E, DevQueries Qs,
             sqto = 0; sqfrom = 0; hto = 0; hfrom = 0; Ld = 0;
 #pragma unroll
             for (int x = 0; x < K; x++) sums[x] = 0.0;
-#pragma unroll
-            for (int z = 0; z < 4; z++) md_prefetch(dp + (size_t)i * RW + 32 * z);
-            s0 = tESCAN;
+            s0 = tEBLK;
             continue;
         }
         if (s1 == tM || s1 == tI) {   // (3.1b2 counts a residue emitted by I_k in the MATCH cell of node k)

@@ -123,17 +123,25 @@ struct witch_ehmm {
     DevBuf<long long> coloff;
     WlDesc *hdesc = nullptr;   // pinned host copy of the work-list descriptor
     // side stream for the multi-domain branch (runs next to the envelope pass of the single-domain regions)
-    cudaStream_t aux = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // (two of them: the batches of a large region list alternate between two halves of the scratch, so that the tail of
+    //  one batch's trace kernel -- its slowest walker -- overlaps with the next batch's Forward kernel)
+    cudaStream_t aux = nullptr, aux2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_md = nullptr, ev_md2 = nullptr;
     void ensure_aux() {
         if (aux) return;
         CUDA_TRY(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&aux2, cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&ev_md, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&ev_md2, cudaEventDisableTiming));
     }
     ~witch_ehmm() {
         if (hdesc) cudaFreeHost(hdesc);
-        if (aux) { cudaStreamDestroy(aux); cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join); }
+        if (aux) {
+            cudaStreamDestroy(aux); cudaStreamDestroy(aux2);
+            cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join); cudaEventDestroy(ev_md); cudaEventDestroy(ev_md2);
+        }
     }
     DevEhmm view() const {
         DevEhmm v;
@@ -187,17 +195,13 @@ static void require_device() {
     if (witch_device_count() <= 0) throw std::runtime_error("no CUDA device available (witch_b200 has no CPU fallback)");
 }
 
-extern "C" int witch_ehmm_create(int n_hmm, const char *const *paths, witch_ehmm **out) {
-    if (n_hmm <= 0 || !paths || !out) return fail(WITCH_ERR_ARG, "witch_ehmm_create: bad arguments");
+// Upload configured profiles to the current device (shared by the text path and the profile-cache path).
+static int ehmm_from_profiles(std::vector<HostProfile> &ps, witch_ehmm **out) {
+    const int n_hmm = (int)ps.size();
     witch_ehmm *e = nullptr;
     try {
-        std::vector<HostProfile> ps;
-        ps.reserve(n_hmm);
-        for (int h = 0; h < n_hmm; h++) {
-            try { ps.push_back(load_profile(paths[h], 0)); }
-            catch (const std::exception &ex) { return fail(WITCH_ERR_IO, ex.what()); }
+        for (int h = 0; h < n_hmm; h++)
             if (ps[h].alph != ps[0].alph) return fail(WITCH_ERR_ARG, "profiles use different alphabets");
-        }
         require_device();
         e = new witch_ehmm();
         CUDA_TRY(cudaGetDevice(&e->device));
@@ -267,6 +271,39 @@ extern "C" int witch_ehmm_create(int n_hmm, const char *const *paths, witch_ehmm
         delete e;
         return fail(WITCH_ERR_CUDA, ex.what());
     }
+}
+extern "C" int witch_ehmm_create(int n_hmm, const char *const *paths, witch_ehmm **out) {
+    if (n_hmm <= 0 || !paths || !out) return fail(WITCH_ERR_ARG, "witch_ehmm_create: bad arguments");
+    std::vector<HostProfile> ps;
+    ps.reserve(n_hmm);
+    for (int h = 0; h < n_hmm; h++) {
+        if (!paths[h]) return fail(WITCH_ERR_ARG, "witch_ehmm_create: null path");
+        try { ps.push_back(load_profile(paths[h], 0)); }
+        catch (const std::exception &ex) { return fail(WITCH_ERR_IO, ex.what()); }
+    }
+    return ehmm_from_profiles(ps, out);
+}
+
+extern "C" int witch_ehmm_create_cached(int n_hmm, const char *const *paths, const char *cache_path, int *cache_hit, witch_ehmm **out) {
+    if (n_hmm <= 0 || !paths || !out || !cache_path) return fail(WITCH_ERR_ARG, "witch_ehmm_create_cached: bad arguments");
+    if (cache_hit) *cache_hit = 0;
+    std::vector<std::string> pv;
+    for (int h = 0; h < n_hmm; h++) {
+        if (!paths[h]) return fail(WITCH_ERR_ARG, "witch_ehmm_create_cached: null path");
+        pv.push_back(paths[h]);
+    }
+    std::vector<HostProfile> ps;
+    if (load_profile_cache(cache_path, pv, ps)) {
+        if (cache_hit) *cache_hit = 1;
+    } else {
+        ps.reserve(n_hmm);
+        for (int h = 0; h < n_hmm; h++) {
+            try { ps.push_back(load_profile(paths[h], 0)); }
+            catch (const std::exception &ex) { return fail(WITCH_ERR_IO, ex.what()); }
+        }
+        save_profile_cache(cache_path, pv, ps);   // (best effort: an unwritable directory only costs the next run its parse)
+    }
+    return ehmm_from_profiles(ps, out);
 }
 extern "C" void witch_ehmm_destroy(witch_ehmm *e) {
     if (!e) return;
@@ -391,10 +428,14 @@ static void launch_parser2(const witch_ehmm *e, const witch_queries *q, int T, P
     CUDA_TRY(cudaGetLastError());
 }
 
-// Parser generation: 1 = one query per CTA (parser_kernel.cuh), 2 = two queries per CTA in packed f32x2 registers with the
-// transition parameters in registers, 3 = the same with the parameters in shared memory (parser2_kernel.cuh).
+// Parser generation (WITCH_PARSER=n overrides; measured on truncated c2, parser Gcell/s: 1 -> 316, 2 -> 305, 3 -> 302,
+// 4 -> 331): 1 = one query per CTA everywhere (parser_kernel.cuh); 2 = two queries per CTA in packed f32x2 registers with the
+// transition parameters in registers (parser2_kernel.cuh) for every C = 4 / C = 8 class; 3 = the same with the parameters
+// in shared memory; 4 = like 2 plus the 224-thread class at 2 CTAs/SM; 5 (default) = the one variant that wins -- two
+// queries per CTA for the C = 8, T <= 224 class (models of 1,025-1,792 nodes: most of a 16S-sized eHMM) at 2 CTAs/SM --
+// and generation 1 everywhere else. All generations give bit-identical results (same arithmetic per query).
 #ifndef WITCH_PARSER_DEFAULT
-#define WITCH_PARSER_DEFAULT 1
+#define WITCH_PARSER_DEFAULT 5
 #endif
 static int parser_generation() {
     static const int g = [] { const char *s = getenv("WITCH_PARSER"); return s ? atoi(s) : WITCH_PARSER_DEFAULT; }();
@@ -440,7 +481,9 @@ static void run_parser(witch_ehmm *e, witch_queries *q, const std::vector<int> &
         wk.dbg_bwd = d_dbg_bwd;
         const int T = classes[ci].T;
         const int gen = d_dbg_bwd ? 1 : parser_generation();
-        if (gen >= 2 && (classes[ci].C == 4 || classes[ci].C == 8) && (classes[ci].C == 4 ? T <= 512 : T <= 384)) {
+        if (gen == 5) {
+            if (classes[ci].C == 8 && T <= 224 && wk.nq >= 2) { launch_parser2<8, 224, 2, false>(e, q, T, wk, st, maxgrid); continue; }
+        } else if (gen >= 2 && (classes[ci].C == 4 || classes[ci].C == 8) && (classes[ci].C == 4 ? T <= 512 : T <= 384)) {
             const bool ps = gen == 3;   // (gen 4: register variant at 2 CTAs/SM, experiment)
             if (classes[ci].C == 4) {
                 if (T <= 256) { if (ps) launch_parser2<4, 256, 2, true>(e, q, T, wk, st, maxgrid); else launch_parser2<4, 256, 2, false>(e, q, T, wk, st, maxgrid); }

@@ -43,8 +43,11 @@ class BatchedSearch:
     index_to_hmm order == order of `hmm_paths`; taxon names are the (already renamed) query names of the reference's
     loadSubQueries (gcmm/loader.py:381-405)."""
 
-    def __init__(self, hmm_paths, num_hmms=10, use_weight=True, runtime_path=None):
-        self.ehmm = api.EHMM(hmm_paths)
+    def __init__(self, hmm_paths, num_hmms=10, use_weight=True, runtime_path=None, profile_cache=None):
+        # profile_cache: e.g. <outdir>/tree_decomp/witch_b200.profiles -- a `-p` re-run over an existing decomposition
+        # (gcmm/gcmm.py:141-152) then skips parsing and configuring the hmmbuild.model.* text again
+        t0 = time.time()
+        self.ehmm = api.EHMM(hmm_paths, cache=profile_cache)
         self.num_hmms = int(num_hmms)
         self.use_weight = use_weight
         self.queries = None
@@ -53,6 +56,8 @@ class BatchedSearch:
         # <outdir>/runtime_breakdown.txt of the reference (configs.py:112-116, written through Configs.runtime): one
         # "(tag) Time to ... (s): <seconds>" line per stage, appended here in the same format when a path is given
         self.runtime_path = runtime_path
+        self._runtime("gpu_load", "load the eHMM onto the GPU (profile cache %s)" % (
+            "hit" if self.ehmm.cache_hit else "miss" if profile_cache else "off"), time.time() - t0)
 
     def _runtime(self, tag, what, seconds):
         if self.runtime_path:
