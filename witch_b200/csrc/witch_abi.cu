@@ -379,10 +379,17 @@ extern "C" int witch_queries_count(const witch_queries *q) { return q ? q->n : 0
 // Family S launch plumbing
 struct SClass { int C, T; std::vector<int> hmms; };
 
-static std::vector<SClass> s_classes(const witch_ehmm *e, const std::vector<int> &hmms) {
+static int parser_generation();
+// shared memory of the generation-6 parser class (C = 16, 128 threads: emission rows + 9 parameter rows of 2,048 columns)
+static size_t parser6_smem(int nsym) { return ((size_t)(nsym + P2_NROWS) * 128 * 16 + PARSER_RED_ROWS * S_RED) * sizeof(float); }
+static std::vector<SClass> s_classes(const witch_ehmm *e, const std::vector<int> &hmms, int nsym) {
     std::map<std::pair<int, int>, std::vector<int>> m;
+    // generation 6 needs two resident CTAs per SM to pay: 2 x (tables + 1 KB reserved) <= 227 KB, i.e. at most 4 distinct
+    // query symbols (plain ACGT/ACGU); query sets with degenerate symbols keep the generation-5 classes
+    const bool gen6 = parser_generation() == 6 && 2 * (parser6_smem(nsym) + 1024) <= 227 * 1024;
     for (int h : hmms) {
         const int M = e->M[h];
+        if (gen6 && M > 1024 && M <= 2048) { m[{16, 128}].push_back(h); continue; }
         if (M > 8192) throw std::runtime_error("model longer than 8192 nodes is not supported");   // (check_limits refuses earlier)
         // C = 16 (3,841 .. 8,192 nodes, e.g. the root of a 16S-sized decomposition): the parameter set no longer fits the
         // register file and spills to local memory -- a slow class for the few models that long, not a fast path
@@ -412,11 +419,12 @@ static void launch_parser(const witch_ehmm *e, const witch_queries *q, int T, Pa
     CUDA_TRY(cudaGetLastError());
 }
 
-template <int C, int MAXT, int MINB, bool PSMEM>
+template <int C, int MAXT, int MINB, bool PSMEM, bool FIXT = false>
 static void launch_parser2(const witch_ehmm *e, const witch_queries *q, int T, ParserWork wk, cudaStream_t st, int maxgrid) {
     const size_t smem = ((size_t)(q->nsym + (PSMEM ? P2_NROWS : 0)) * T * C + PARSER_RED_ROWS * S_RED) * sizeof(float);
     if (smem > 220 * 1024) throw std::runtime_error("emission + parameter tables do not fit shared memory");
-    auto kern = mh_parser2_kernel<C, MAXT, MINB, PSMEM>;
+    auto kern = mh_parser2_kernel<C, MAXT, MINB, PSMEM, FIXT>;
+    if (FIXT) T = MAXT;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, smem));
@@ -433,9 +441,13 @@ static void launch_parser2(const witch_ehmm *e, const witch_queries *q, int T, P
 // transition parameters in registers (parser2_kernel.cuh) for every C = 4 / C = 8 class; 3 = the same with the parameters
 // in shared memory; 4 = like 2 plus the 224-thread class at 2 CTAs/SM; 5 (default) = the one variant that wins -- two
 // queries per CTA for the C = 8, T <= 224 class (models of 1,025-1,792 nodes: most of a 16S-sized eHMM) at 2 CTAs/SM --
-// and generation 1 everywhere else. All generations give bit-identical results (same arithmetic per query).
+// and generation 1 everywhere else; 6 (default) = like 5, but models of 1,025-2,048 nodes get 16 columns per thread in
+// 128-thread CTAs with the transition parameters in shared memory (245 registers, no spills, 2 CTAs/SM; half the warp
+// instructions per cell of generation 1; measured 348 vs 329 Gcell/s) whenever the query set has only the 4 canonical
+// symbols (s_classes). Generations 1-5 give bit-identical results (same arithmetic per query); generation 6 sums a row's
+// columns in a different association (16 instead of 8 per thread): scores differ by <= 2.5e-4 bits.
 #ifndef WITCH_PARSER_DEFAULT
-#define WITCH_PARSER_DEFAULT 5
+#define WITCH_PARSER_DEFAULT 6
 #endif
 static int parser_generation() {
     static const int g = [] { const char *s = getenv("WITCH_PARSER"); return s ? atoi(s) : WITCH_PARSER_DEFAULT; }();
@@ -454,7 +466,7 @@ static void run_parser(witch_ehmm *e, witch_queries *q, const std::vector<int> &
     int maxgrid = e->num_sms * 8;
     e->scratch.alloc((size_t)maxgrid * 2 * PARSER_SCRATCH_ROWS * (size_t)((Lcap + 4) & ~3) + 64);   // (two queries per CTA in generation 2/3)
     e->counter.alloc(64);
-    auto classes = s_classes(e, hsel);
+    auto classes = s_classes(e, hsel, q->nsym);
     std::vector<int> allh;
     std::vector<int> hoff;
     for (auto &c : classes) {
@@ -481,7 +493,8 @@ static void run_parser(witch_ehmm *e, witch_queries *q, const std::vector<int> &
         wk.dbg_bwd = d_dbg_bwd;
         const int T = classes[ci].T;
         const int gen = d_dbg_bwd ? 1 : parser_generation();
-        if (gen == 5) {
+        if (gen == 6 && classes[ci].C == 16 && T == 128 && wk.nq >= 2) { launch_parser2<16, 128, 2, true, true>(e, q, T, wk, st, maxgrid); continue; }
+        if (gen == 5 || gen == 6) {
             if (classes[ci].C == 8 && T <= 224 && wk.nq >= 2) { launch_parser2<8, 224, 2, false>(e, q, T, wk, st, maxgrid); continue; }
         } else if (gen >= 2 && (classes[ci].C == 4 || classes[ci].C == 8) && (classes[ci].C == 4 ? T <= 512 : T <= 384)) {
             const bool ps = gen == 3;   // (gen 4: register variant at 2 CTAs/SM, experiment)
