@@ -108,10 +108,6 @@ __device__ __forceinline__ void parser_decode_regions(float *Fs, float *Bs, int 
     }
 }
 
-#ifndef WITCH_P2_CHAIN1
-#define WITCH_P2_CHAIN1 0
-#endif
-constexpr bool P2_CHAIN1 = WITCH_P2_CHAIN1 != 0;   // Forward local D chain with the match term as an off-chain product
 // shared-memory parameter rows (PSMEM): [9][C/4][T][4] floats, row order below
 enum { P2_A = 0, P2_B, P2_G, P2_MD, P2_DD, P2_MI, P2_II, P2_EN, P2_PDD, P2_NROWS };
 
@@ -357,10 +353,7 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser2_kernel(DevEhmm E, DevQu
                 if (PSMEM) { ldp(P2_MD, qmd_); ldp(P2_DD, qdd_); }
                 dl[0] = p2b(0.f);
 #pragma unroll
-                for (int c = 1; c < C; c++) {
-                    if (P2_CHAIN1) dl[c] = p2_fma(dl[c - 1], p2b(PSMEM ? qdd_[c] : rdd[c]), p2_mul(nM[c - 1], p2b(PSMEM ? qmd_[c] : rmd[c])));   // one dependent op per link
-                    else dl[c] = p2_fma(nM[c - 1], p2b(PSMEM ? qmd_[c] : rmd[c]), p2_mul(dl[c - 1], p2b(PSMEM ? qdd_[c] : rdd[c])));
-                }
+                for (int c = 1; c < C; c++) dl[c] = p2_fma(nM[c - 1], p2b(PSMEM ? qmd_[c] : rmd[c]), p2_mul(dl[c - 1], p2b(PSMEM ? qdd_[c] : rdd[c])));
             }
             const float2 yl = p2_fma(nM[C - 1], p2b(mdo), p2_mul(dl[C - 1], p2b(ddo)));
             float2 at = p2b(0.f);

@@ -496,6 +496,9 @@ static void run_parser(witch_ehmm *e, witch_queries *q, const std::vector<int> &
         if (gen == 6 && classes[ci].C == 16 && T == 128 && wk.nq >= 2) { launch_parser2<16, 128, 2, true, true>(e, q, T, wk, st, maxgrid); continue; }
         if (gen == 5 || gen == 6) {
             if (classes[ci].C == 8 && T <= 224 && wk.nq >= 2) { launch_parser2<8, 224, 2, false>(e, q, T, wk, st, maxgrid); continue; }
+            // models of at most 1,024 nodes (protein families, short markers): two packed queries per CTA, parameters in
+            // registers (128 registers, no spills; c4 sample: 248 vs 193 Gcell/s, bit-identical)
+            if (gen == 6 && classes[ci].C == 4 && T <= 256 && wk.nq >= 2) { launch_parser2<4, 256, 2, false>(e, q, T, wk, st, maxgrid); continue; }
         } else if (gen >= 2 && (classes[ci].C == 4 || classes[ci].C == 8) && (classes[ci].C == 4 ? T <= 512 : T <= 384)) {
             const bool ps = gen == 3;   // (gen 4: register variant at 2 CTAs/SM, experiment)
             if (classes[ci].C == 4) {
