@@ -108,13 +108,27 @@ __device__ __forceinline__ void parser_decode_regions(float *Fs, float *Bs, int 
     }
 }
 
-// shared-memory parameter rows (PSMEM): [9][C/4][T][4] floats, row order below
+// shared-memory parameter rows, each laid out like an emission row: [C/4][T][4] floats + [T][C%4] tail. PMODE selects where
+// the 9 per-column parameter sets of a thread live: 0 = registers (loaded once per item), 1 = all in shared memory (one
+// LDS.128 per 4 columns and use), 2 = hybrid: the six that sit on the row's dependency chain (MM, IM, DM, MD, DD, the DD
+// products) in registers, the three that do not (MI, II, entry) in shared memory.
 enum { P2_A = 0, P2_B, P2_G, P2_MD, P2_DD, P2_MI, P2_II, P2_EN, P2_PDD, P2_NROWS };
+__host__ __device__ constexpr int p2_smem_rows(int pmode) { return pmode == 1 ? (int)P2_NROWS : pmode == 2 ? 3 : 0; }
+__host__ __device__ constexpr int p2_slot(int pmode, int row) { return pmode == 1 ? row : row - P2_MI; }   // hybrid: MI, II, EN -> 0, 1, 2
+// element (thread j, column cc) of a row in the vector + tail layout
+template <int C>
+__device__ __forceinline__ int p2_index(int T, int j, int cc) {
+    constexpr int V = C / 4, R = C % 4;
+    return cc < 4 * V ? (cc >> 2) * (T * 4) + j * 4 + (cc & 3) : V * T * 4 + j * R + (cc - 4 * V);
+}
 
 // FIXT: the CTA always has MAXT threads, so every shared-memory offset of the row loops is an immediate
-template <int C, int MAXT, int MINB, bool PSMEM, bool FIXT = false>
+template <int C, int MAXT, int MINB, int PMODE, bool FIXT = false>
 __global__ void __launch_bounds__(MAXT, MINB) mh_parser2_kernel(DevEhmm E, DevQueries Q, ParserWork Wk) {
-    static_assert(C % 4 == 0, "packed parser: C must be a multiple of 4");
+    static_assert(C >= 4, "packed parser: at least one vector group of columns");
+    constexpr bool PSMEM = PMODE == 1;     // hot rows (A, B, G, MD, DD, PDD) in shared memory
+    constexpr bool PCOLD = PMODE >= 1;     // cold rows (MI, II, EN) in shared memory
+    constexpr int V = C / 4, R = C % 4;
     WITCH_DYN_SMEM(float, smem);
     int T = FIXT ? MAXT : (int)blockDim.x, tid = threadIdx.x;
     if (!FIXT) PIN32(T);
@@ -124,7 +138,7 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser2_kernel(DevEhmm E, DevQu
     const int TC = T * C;
     float *emis_s = smem;                                        // [nsym][TC]
     float *par_s = emis_s + (size_t)Q.nsym * TC;                 // [9][TC] (PSMEM only)
-    float *s_red = par_s + (PSMEM ? (size_t)P2_NROWS * TC : 0);  // reduction area
+    float *s_red = par_s + (size_t)p2_smem_rows(PMODE) * TC;     // reduction area
     float2 *r2 = reinterpret_cast<float2 *>(s_red);              // per-row exchange, float2 per warp, double-buffered by row parity
     float *rc = s_red + 2 * 160;                                 // HMM constants per warp: PW[16], KW[16], AC[16]
 #define R_TOT(par, x) r2[(par) * 16 + (x)]
@@ -136,8 +150,9 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser2_kernel(DevEhmm E, DevQu
 #define R_KW(x) rc[16 + (x)]
 #define R_AC(x) rc[32 + (x)]
     __shared__ int s_item;
-    const unsigned emis_ta = smem_u32(emis_s) + tid * 16;
-    const unsigned par_ta = smem_u32(par_s) + tid * 16;
+    const unsigned emis_ta = smem_u32(emis_s) + tid * 16;                      // vector part of this thread's columns
+    const unsigned emis_tt = smem_u32(emis_s) + V * T * 16 + tid * (R * 4);     // tail part (C % 4 columns)
+    const unsigned par_ta = smem_u32(par_s) + tid * 16, par_tt = smem_u32(par_s) + V * T * 16 + tid * (R * 4);
     const unsigned erow_b = TC * 4, estep = T * 16;
 
     const int Lr = (Wk.Lcap + 4) & ~3;
@@ -150,14 +165,30 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser2_kernel(DevEhmm E, DevQu
     const long long nitems = (long long)Wk.nh * npairs;
     int loaded_h = -1;
     // parameter access: registers (loaded once per item) or shared memory (one LDS.128 per 4 columns and use)
-    float ra[PSMEM ? 1 : C], rb[PSMEM ? 1 : C], rg[PSMEM ? 1 : C], rmd[PSMEM ? 1 : C], rdd[PSMEM ? 1 : C], rmi[PSMEM ? 1 : C],
-        rii[PSMEM ? 1 : C], ren[PSMEM ? 1 : C], rpDD[PSMEM ? 1 : C];
-    auto ldp = [&](const int row, float (&dst)[C]) {   // PSMEM: fetch one parameter row of this thread's columns
+    float ra[PSMEM ? 1 : C], rb[PSMEM ? 1 : C], rg[PSMEM ? 1 : C], rmd[PSMEM ? 1 : C], rdd[PSMEM ? 1 : C], rmi[PCOLD ? 1 : C],
+        rii[PCOLD ? 1 : C], ren[PCOLD ? 1 : C], rpDD[PSMEM ? 1 : C];
+    auto ldp = [&](const int row, float (&dst)[C]) {   // fetch one shared-memory parameter row of this thread's columns
+        const unsigned ro = p2_slot(PMODE, row) * erow_b;
 #pragma unroll
-        for (int v = 0; v < C / 4; v++) {
-            const float4 t4 = p2_lds4v(par_ta + (row * (C / 4) + v) * estep);
+        for (int v = 0; v < V; v++) {
+            const float4 t4 = p2_lds4v(par_ta + ro + v * estep);
             dst[4 * v] = t4.x; dst[4 * v + 1] = t4.y; dst[4 * v + 2] = t4.z; dst[4 * v + 3] = t4.w;
         }
+#pragma unroll
+        for (int r = 0; r < R; r++) dst[4 * V + r] = lds_f1v(par_tt + ro + 4 * r);
+    };
+    // emission odds of this thread's columns for the residue codes xa / xb of the two queries
+    auto lde = [&](const int xa, const int xb, float (&da)[C], float (&db)[C]) {
+        const unsigned a0 = emis_ta + xa * erow_b, b0 = emis_ta + xb * erow_b;
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+            const float4 t4 = lds_f4(a0 + v * estep), u4 = lds_f4(b0 + v * estep);
+            da[4 * v] = t4.x; da[4 * v + 1] = t4.y; da[4 * v + 2] = t4.z; da[4 * v + 3] = t4.w;
+            db[4 * v] = u4.x; db[4 * v + 1] = u4.y; db[4 * v + 2] = u4.z; db[4 * v + 3] = u4.w;
+        }
+        const unsigned a1 = emis_tt + xa * erow_b, b1 = emis_tt + xb * erow_b;
+#pragma unroll
+        for (int r = 0; r < R; r++) { da[4 * V + r] = lds_f1(a1 + 4 * r); db[4 * V + r] = lds_f1(b1 + 4 * r); }
     };
     for (;;) {
         __syncthreads();
@@ -188,7 +219,7 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser2_kernel(DevEhmm E, DevQu
                 int x = idx / TC, col = idx - x * TC;
                 int j = col / C, cc = col - j * C;
                 float v = (col < st - 1) ? __ldg(eg + (size_t)Q.symrow[x] * st + 1 + col) : 0.f;
-                emis_s[(size_t)x * TC + emis_index<C>(T, j, cc)] = v;
+                emis_s[(size_t)x * TC + p2_index<C>(T, j, cc)] = v;
             }
             loaded_h = h;
         }
@@ -240,17 +271,15 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser2_kernel(DevEhmm E, DevQu
             if (lane == 31) { R_PW(w) = Pc; R_AC(w) = pDD[C - 1] * Cexcl; }
             if (lane == 0) R_KW(w) = kw;
         }
-        if (PSMEM) {   // forward parameter rows -> shared memory
 #pragma unroll
-            for (int c = 0; c < C; c++) {
-                const int ix = emis_index<C>(T, tid, c);
-                par_s[P2_A * TC + ix] = pa[c]; par_s[P2_B * TC + ix] = pb[c]; par_s[P2_G * TC + ix] = pg[c]; par_s[P2_MD * TC + ix] = pmd[c];
-                par_s[P2_DD * TC + ix] = pdd[c]; par_s[P2_MI * TC + ix] = pmi[c]; par_s[P2_II * TC + ix] = pii[c]; par_s[P2_EN * TC + ix] = pen[c];
-                par_s[P2_PDD * TC + ix] = pDD[c];
-            }
-        } else {
-#pragma unroll
-            for (int c = 0; c < C; c++) { ra[c] = pa[c]; rb[c] = pb[c]; rg[c] = pg[c]; rmd[c] = pmd[c]; rdd[c] = pdd[c]; rmi[c] = pmi[c]; rii[c] = pii[c]; ren[c] = pen[c]; rpDD[c] = pDD[c]; }
+        for (int c = 0; c < C; c++) {   // forward parameter rows -> shared memory / registers
+            const int ix = p2_index<C>(T, tid, c);
+            if (PSMEM) {
+                par_s[p2_slot(PMODE, P2_A) * TC + ix] = pa[c]; par_s[p2_slot(PMODE, P2_B) * TC + ix] = pb[c]; par_s[p2_slot(PMODE, P2_G) * TC + ix] = pg[c];
+                par_s[p2_slot(PMODE, P2_MD) * TC + ix] = pmd[c]; par_s[p2_slot(PMODE, P2_DD) * TC + ix] = pdd[c]; par_s[p2_slot(PMODE, P2_PDD) * TC + ix] = pDD[c];
+            } else { ra[c] = pa[c]; rb[c] = pb[c]; rg[c] = pg[c]; rmd[c] = pmd[c]; rdd[c] = pdd[c]; rpDD[c] = pDD[c]; }
+            if (PCOLD) { par_s[p2_slot(PMODE, P2_MI) * TC + ix] = pmi[c]; par_s[p2_slot(PMODE, P2_II) * TC + ix] = pii[c]; par_s[p2_slot(PMODE, P2_EN) * TC + ix] = pen[c]; }
+            else { rmi[c] = pmi[c]; rii[c] = pii[c]; ren[c] = pen[c]; }
         }
         const float pDDlast = pDD[C - 1];
         __syncthreads();
@@ -318,15 +347,7 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser2_kernel(DevEhmm E, DevQu
                 if (i - 1 == LBe) { capC = xC.y; capS = sFB; }
             }
             float ea[C], eb[C];
-            {
-                const unsigned a0 = emis_ta + xrA * erow_b, b0 = emis_ta + xrB * erow_b;
-#pragma unroll
-                for (int v = 0; v < C / 4; v++) {
-                    const float4 t4 = lds_f4(a0 + v * estep), u4 = lds_f4(b0 + v * estep);
-                    ea[4 * v] = t4.x; ea[4 * v + 1] = t4.y; ea[4 * v + 2] = t4.z; ea[4 * v + 3] = t4.w;
-                    eb[4 * v] = u4.x; eb[4 * v + 1] = u4.y; eb[4 * v + 2] = u4.z; eb[4 * v + 3] = u4.w;
-                }
-            }
+            lde(xrA, xrB, ea, eb);
             if (i < L) { xrA = qdA[i]; xrB = qdBe[min(i, LBe - 1)]; }
             float2 mL = p2_up(sM[C - 1], 1), iL = p2_up(sI[C - 1], 1);
             if (lane == 0) {
@@ -336,11 +357,12 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser2_kernel(DevEhmm E, DevQu
             float2 nM[C];
             {
                 float qa_[C], qb_[C], qg_[C], qmi_[C], qii_[C], qen_[C];
-                if (PSMEM) { ldp(P2_A, qa_); ldp(P2_B, qb_); ldp(P2_G, qg_); ldp(P2_MI, qmi_); ldp(P2_II, qii_); ldp(P2_EN, qen_); }
+                if (PSMEM) { ldp(P2_A, qa_); ldp(P2_B, qb_); ldp(P2_G, qg_); }
+                if (PCOLD) { ldp(P2_MI, qmi_); ldp(P2_II, qii_); ldp(P2_EN, qen_); }
 #pragma unroll
                 for (int c = C - 1; c >= 0; c--) {
                     const float2 pm = c > 0 ? sM[c - 1] : mL, pi = c > 0 ? sI[c - 1] : iL, pd = c > 0 ? sD[c - 1] : dL;
-                    const float tmi = PSMEM ? qmi_[c] : rmi[c], tii = PSMEM ? qii_[c] : rii[c], ten = PSMEM ? qen_[c] : ren[c];
+                    const float tmi = PCOLD ? qmi_[c] : rmi[c], tii = PCOLD ? qii_[c] : rii[c], ten = PCOLD ? qen_[c] : ren[c];
                     const float ta_ = PSMEM ? qa_[c] : ra[c], tb_ = PSMEM ? qb_[c] : rb[c], tg_ = PSMEM ? qg_[c] : rg[c];
                     sI[c] = p2_fma(sM[c], p2b(tmi), p2_mul(sI[c], p2b(tii)));
                     float2 acc = p2_mul(xB, p2b(ten));
@@ -414,7 +436,7 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser2_kernel(DevEhmm E, DevQu
         if (PSMEM) {   // backward rows: MM, IM, DM, MD, DD of the owned columns (MI, II, entry are already in place)
 #pragma unroll
             for (int c = 0; c < C; c++) {
-                const int ix = emis_index<C>(T, tid, c);
+                const int ix = p2_index<C>(T, tid, c);
                 par_s[P2_A * TC + ix] = pa[c]; par_s[P2_B * TC + ix] = pb[c]; par_s[P2_G * TC + ix] = pg[c]; par_s[P2_MD * TC + ix] = pmd[c];
                 par_s[P2_DD * TC + ix] = pdd[c];
             }
@@ -438,12 +460,10 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser2_kernel(DevEhmm E, DevQu
             if (i < L) {
                 const int xa = qdA[i], xb = qdBe[min(i, LBe - 1)];
                 const unsigned a0 = emis_ta + xa * erow_b, b0 = emis_ta + xb * erow_b;
+                float ea[C], eb[C];
+                lde(xa, xb, ea, eb);
 #pragma unroll
-                for (int v = 0; v < C / 4; v++) {
-                    const float4 t4 = lds_f4(a0 + v * estep), u4 = lds_f4(b0 + v * estep);
-                    mn[4 * v] = p2(sM[4 * v].x * t4.x, sM[4 * v].y * u4.x); mn[4 * v + 1] = p2(sM[4 * v + 1].x * t4.y, sM[4 * v + 1].y * u4.y);
-                    mn[4 * v + 2] = p2(sM[4 * v + 2].x * t4.z, sM[4 * v + 2].y * u4.z); mn[4 * v + 3] = p2(sM[4 * v + 3].x * t4.w, sM[4 * v + 3].y * u4.w);
-                }
+                for (int c = 0; c < C; c++) mn[c] = p2(sM[c].x * ea[c], sM[c].y * eb[c]);
                 if (tid + 1 < T) eR = p2(lds_f1(a0 + 16), lds_f1(b0 + 16));
             } else {
 #pragma unroll
@@ -455,16 +475,17 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser2_kernel(DevEhmm E, DevQu
             float2 Mp[C], nI[C], tm[C];
             {
                 float qen_[C], qa_[C], qb_[C], qg_[C], qmi_[C], qii_[C];
-                if (PSMEM) { ldp(P2_EN, qen_); ldp(P2_A, qa_); ldp(P2_B, qb_); ldp(P2_G, qg_); ldp(P2_MI, qmi_); ldp(P2_II, qii_); }
+                if (PSMEM) { ldp(P2_A, qa_); ldp(P2_B, qb_); ldp(P2_G, qg_); }
+                if (PCOLD) { ldp(P2_EN, qen_); ldp(P2_MI, qmi_); ldp(P2_II, qii_); }
 #pragma unroll
                 for (int c = 0; c < C; c++) {
                     mnR[c] = (c < C - 1) ? mn[c + 1] : nb;
-                    bp = p2_fma(mn[c], p2b(PSMEM ? qen_[c] : ren[c]), bp);
+                    bp = p2_fma(mn[c], p2b(PCOLD ? qen_[c] : ren[c]), bp);
                 }
 #pragma unroll
                 for (int c = 0; c < C; c++) {
-                    Mp[c] = p2_fma(mnR[c], p2b(PSMEM ? qa_[c] : ra[c]), p2_mul(sI[c], p2b(PSMEM ? qmi_[c] : rmi[c])));
-                    nI[c] = p2_fma(mnR[c], p2b(PSMEM ? qb_[c] : rb[c]), p2_mul(sI[c], p2b(PSMEM ? qii_[c] : rii[c])));
+                    Mp[c] = p2_fma(mnR[c], p2b(PSMEM ? qa_[c] : ra[c]), p2_mul(sI[c], p2b(PCOLD ? qmi_[c] : rmi[c])));
+                    nI[c] = p2_fma(mnR[c], p2b(PSMEM ? qb_[c] : rb[c]), p2_mul(sI[c], p2b(PCOLD ? qii_[c] : rii[c])));
                     tm[c] = p2_mul(mnR[c], p2b(PSMEM ? qg_[c] : rg[c]));
                 }
             }

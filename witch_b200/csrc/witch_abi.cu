@@ -380,16 +380,19 @@ extern "C" int witch_queries_count(const witch_queries *q) { return q ? q->n : 0
 struct SClass { int C, T; std::vector<int> hmms; };
 
 static int parser_generation();
-// shared memory of the generation-6 parser class (C = 16, 128 threads: emission rows + 9 parameter rows of 2,048 columns)
-static size_t parser6_smem(int nsym) { return ((size_t)(nsym + P2_NROWS) * 128 * 16 + PARSER_RED_ROWS * S_RED) * sizeof(float); }
-static std::vector<SClass> s_classes(const witch_ehmm *e, const std::vector<int> &hmms, int nsym) {
+// shared memory of the generation-6 parser classes (128 threads x C columns: emission rows + the parameter rows kept in smem)
+static size_t parser6_smem(int nsym, int C, int pmode) { return ((size_t)(nsym + p2_smem_rows(pmode)) * 128 * C + PARSER_RED_ROWS * S_RED) * sizeof(float); }
+static std::vector<SClass> s_classes(const witch_ehmm *e, const std::vector<int> &hmms, int nsym, bool allow6 = true) {
     std::map<std::pair<int, int>, std::vector<int>> m;
-    // generation 6 needs two resident CTAs per SM to pay: 2 x (tables + 1 KB reserved) <= 227 KB, i.e. at most 4 distinct
-    // query symbols (plain ACGT/ACGU); query sets with degenerate symbols keep the generation-5 classes
-    const bool gen6 = parser_generation() == 6 && 2 * (parser6_smem(nsym) + 1024) <= 227 * 1024;
+    // generation 6 needs two resident CTAs per SM to pay: 2 x (tables + 1 KB reserved) <= 227 KB. C = 13 (hybrid: 3 parameter
+    // rows in smem): up to 13 distinct query symbols; C = 16 (all 9 parameter rows in smem): the 4 canonical ones only
+    const bool g6 = allow6 && parser_generation() == 6;
+    const bool gen6_13 = g6 && 2 * (parser6_smem(nsym, 13, 2) + 1024) <= 227 * 1024;
+    const bool gen6_16 = g6 && 2 * (parser6_smem(nsym, 16, 1) + 1024) <= 227 * 1024;
     for (int h : hmms) {
         const int M = e->M[h];
-        if (gen6 && M > 1024 && M <= 2048) { m[{16, 128}].push_back(h); continue; }
+        if (gen6_13 && M > 1024 && M <= 13 * 128) { m[{13, 128}].push_back(h); continue; }
+        if (gen6_16 && M > 13 * 128 && M <= 2048) { m[{16, 128}].push_back(h); continue; }
         if (M > 8192) throw std::runtime_error("model longer than 8192 nodes is not supported");   // (check_limits refuses earlier)
         // C = 16 (3,841 .. 8,192 nodes, e.g. the root of a 16S-sized decomposition): the parameter set no longer fits the
         // register file and spills to local memory -- a slow class for the few models that long, not a fast path
@@ -419,11 +422,11 @@ static void launch_parser(const witch_ehmm *e, const witch_queries *q, int T, Pa
     CUDA_TRY(cudaGetLastError());
 }
 
-template <int C, int MAXT, int MINB, bool PSMEM, bool FIXT = false>
+template <int C, int MAXT, int MINB, int PMODE, bool FIXT = false>
 static void launch_parser2(const witch_ehmm *e, const witch_queries *q, int T, ParserWork wk, cudaStream_t st, int maxgrid) {
-    const size_t smem = ((size_t)(q->nsym + (PSMEM ? P2_NROWS : 0)) * T * C + PARSER_RED_ROWS * S_RED) * sizeof(float);
+    const size_t smem = ((size_t)(q->nsym + p2_smem_rows(PMODE)) * T * C + PARSER_RED_ROWS * S_RED) * sizeof(float);
     if (smem > 220 * 1024) throw std::runtime_error("emission + parameter tables do not fit shared memory");
-    auto kern = mh_parser2_kernel<C, MAXT, MINB, PSMEM, FIXT>;
+    auto kern = mh_parser2_kernel<C, MAXT, MINB, PMODE, FIXT>;
     if (FIXT) T = MAXT;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
@@ -466,7 +469,7 @@ static void run_parser(witch_ehmm *e, witch_queries *q, const std::vector<int> &
     int maxgrid = e->num_sms * 8;
     e->scratch.alloc((size_t)maxgrid * 2 * PARSER_SCRATCH_ROWS * (size_t)((Lcap + 4) & ~3) + 64);   // (two queries per CTA in generation 2/3)
     e->counter.alloc(64);
-    auto classes = s_classes(e, hsel, q->nsym);
+    auto classes = s_classes(e, hsel, q->nsym, /*allow6=*/d_dbg_bwd == nullptr && qsel.size() >= 2);
     std::vector<int> allh;
     std::vector<int> hoff;
     for (auto &c : classes) {
@@ -493,6 +496,7 @@ static void run_parser(witch_ehmm *e, witch_queries *q, const std::vector<int> &
         wk.dbg_bwd = d_dbg_bwd;
         const int T = classes[ci].T;
         const int gen = d_dbg_bwd ? 1 : parser_generation();
+        if (gen == 6 && classes[ci].C == 13 && T == 128 && wk.nq >= 2) { launch_parser2<13, 128, 2, 2, true>(e, q, T, wk, st, maxgrid); continue; }
         if (gen == 6 && classes[ci].C == 16 && T == 128 && wk.nq >= 2) { launch_parser2<16, 128, 2, true, true>(e, q, T, wk, st, maxgrid); continue; }
         if (gen == 5 || gen == 6) {
             if (classes[ci].C == 8 && T <= 224 && wk.nq >= 2) { launch_parser2<8, 224, 2, false>(e, q, T, wk, st, maxgrid); continue; }
