@@ -378,9 +378,10 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser2_kernel(DevEhmm E, DevQu
                 for (int c = 1; c < C; c++) dl[c] = p2_fma(nM[c - 1], p2b(PSMEM ? qmd_[c] : rmd[c]), p2_mul(dl[c - 1], p2b(PSMEM ? qdd_[c] : rdd[c])));
             }
             const float2 yl = p2_fma(nM[C - 1], p2b(mdo), p2_mul(dl[C - 1], p2b(ddo)));
-            float2 at = p2b(0.f);
+            float2 at4[4] = {p2b(0.f), p2b(0.f), p2b(0.f), p2b(0.f)};   // four partial sums: no 13-deep chain of dependent adds
 #pragma unroll
-            for (int c = 0; c < C; c++) { sM[c] = nM[c]; at = p2_add(at, p2_add(nM[c], dl[c])); }
+            for (int c = 0; c < C; c++) { sM[c] = nM[c]; at4[c & 3] = p2_add(at4[c & 3], p2_add(nM[c], dl[c])); }
+            const float2 at = p2_add(p2_add(at4[0], at4[1]), p2_add(at4[2], at4[3]));
             float2 y = yl, v = p2_fma(yl, p2b(Rt), at);
 #pragma unroll
             for (int s = 0; s < 5; s++) {
@@ -471,7 +472,7 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser2_kernel(DevEhmm E, DevQu
             }
             float2 nb = p2_down(mn[0], 1);
             if (lane == 31) nb = (w + 1 < NW && i < L) ? p2_mul(R_BM((i + 1) & 1, w + 1), eR) : p2b(0.f);
-            float2 bp = p2b(0.f);
+            float2 bp4[4] = {p2b(0.f), p2b(0.f), p2b(0.f), p2b(0.f)};
             float2 Mp[C], nI[C], tm[C];
             {
                 float qen_[C], qa_[C], qb_[C], qg_[C], qmi_[C], qii_[C];
@@ -480,7 +481,7 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser2_kernel(DevEhmm E, DevQu
 #pragma unroll
                 for (int c = 0; c < C; c++) {
                     mnR[c] = (c < C - 1) ? mn[c + 1] : nb;
-                    bp = p2_fma(mn[c], p2b(PCOLD ? qen_[c] : ren[c]), bp);
+                    bp4[c & 3] = p2_fma(mn[c], p2b(PCOLD ? qen_[c] : ren[c]), bp4[c & 3]);
                 }
 #pragma unroll
                 for (int c = 0; c < C; c++) {
@@ -489,6 +490,7 @@ __global__ void __launch_bounds__(MAXT, MINB) mh_parser2_kernel(DevEhmm E, DevQu
                     tm[c] = p2_mul(mnR[c], p2b(PSMEM ? qg_[c] : rg[c]));
                 }
             }
+            float2 bp = p2_add(p2_add(bp4[0], bp4[1]), p2_add(bp4[2], bp4[3]));
             float qdd_[C], qmd_[C];
             if (PSMEM) { ldp(P2_DD, qdd_); ldp(P2_MD, qmd_); }
             float2 y = tm[C - 1];

@@ -392,6 +392,8 @@ static std::vector<SClass> s_classes(const witch_ehmm *e, const std::vector<int>
     for (int h : hmms) {
         const int M = e->M[h];
         if (gen6_13 && M > 1024 && M <= 13 * 128) { m[{13, 128}].push_back(h); continue; }
+        // models of 2,049-3,328 nodes (the root of a 16S-sized decomposition): the same kernel with 256 threads, one CTA per SM
+        if (g6 && parser6_smem(nsym, 13, 2) * 2 + 1024 <= 227 * 1024 && M > 2048 && M <= 13 * 256) { m[{13, 256}].push_back(h); continue; }
         if (gen6_16 && M > 13 * 128 && M <= 2048) { m[{16, 128}].push_back(h); continue; }
         if (M > 8192) throw std::runtime_error("model longer than 8192 nodes is not supported");   // (check_limits refuses earlier)
         // C = 16 (3,841 .. 8,192 nodes, e.g. the root of a 16S-sized decomposition): the parameter set no longer fits the
@@ -439,16 +441,21 @@ static void launch_parser2(const witch_ehmm *e, const witch_queries *q, int T, P
     CUDA_TRY(cudaGetLastError());
 }
 
-// Parser generation (WITCH_PARSER=n overrides; measured on truncated c2, parser Gcell/s: 1 -> 316, 2 -> 305, 3 -> 302,
-// 4 -> 331): 1 = one query per CTA everywhere (parser_kernel.cuh); 2 = two queries per CTA in packed f32x2 registers with the
-// transition parameters in registers (parser2_kernel.cuh) for every C = 4 / C = 8 class; 3 = the same with the parameters
-// in shared memory; 4 = like 2 plus the 224-thread class at 2 CTAs/SM; 5 (default) = the one variant that wins -- two
-// queries per CTA for the C = 8, T <= 224 class (models of 1,025-1,792 nodes: most of a 16S-sized eHMM) at 2 CTAs/SM --
-// and generation 1 everywhere else; 6 (default) = like 5, but models of 1,025-2,048 nodes get 16 columns per thread in
-// 128-thread CTAs with the transition parameters in shared memory (245 registers, no spills, 2 CTAs/SM; half the warp
-// instructions per cell of generation 1; measured 348 vs 329 Gcell/s) whenever the query set has only the 4 canonical
-// symbols (s_classes). Generations 1-5 give bit-identical results (same arithmetic per query); generation 6 sums a row's
-// columns in a different association (16 instead of 8 per thread): scores differ by <= 2.5e-4 bits.
+// Parser generation (WITCH_PARSER=n overrides the default):
+//   1 = one query per CTA everywhere (parser_kernel.cuh; the round-1 kernel: 316-330 Gcell/s on truncated c2);
+//   5 = two packed queries per CTA (parser2_kernel.cuh, parameters in registers) for the C = 8, T <= 224 class (models of
+//       1,025-1,792 nodes) -- capped at 128 registers by its 14 warps/SM, it spills: 330 Gcell/s;
+//   6 (default) = two packed queries per CTA in 128-thread CTAs that own MORE columns per thread, 2 CTAs/SM at 245
+//       registers without spills (s_classes): 13 columns per thread with the six on-chain parameter sets in registers and
+//       MI/II/entry in shared memory for models of 1,025-1,664 nodes (458 Gcell/s on truncated c2, 475 on full c2) and, with
+//       256 threads, of 2,049-3,328 nodes; 16 columns per thread with all parameters in shared memory for 1,665-2,048
+//       nodes (348 Gcell/s; plain-ACGT query sets only); the C = 4 classes (<= 1,024 nodes) run the register variant
+//       with two packed queries (c4 sample: 248 vs 193 Gcell/s). Whatever does not fit falls back to 5, then 1.
+// Measured and dropped (round 2): packed pairs for every C = 8 class with parameters in registers (305) or in shared
+// memory (302), 12 columns x 160 threads (294: 168-register cap, spills), 9 columns x 192 threads (417), the local D chain
+// with one dependent FFMA per link (no change), four partial sums for the row sums (no change, kept).
+// Generations 1 and 5 give bit-identical results; generation 6 sums a row's columns in another association (13 or 16
+// per thread instead of 8): scores differ by <= 2.5e-4 bits.
 #ifndef WITCH_PARSER_DEFAULT
 #define WITCH_PARSER_DEFAULT 6
 #endif
@@ -496,25 +503,14 @@ static void run_parser(witch_ehmm *e, witch_queries *q, const std::vector<int> &
         wk.dbg_bwd = d_dbg_bwd;
         const int T = classes[ci].T;
         const int gen = d_dbg_bwd ? 1 : parser_generation();
+        if (gen == 6 && classes[ci].C == 13 && T == 256 && wk.nq >= 2) { launch_parser2<13, 256, 1, 2, true>(e, q, T, wk, st, maxgrid); continue; }
         if (gen == 6 && classes[ci].C == 13 && T == 128 && wk.nq >= 2) { launch_parser2<13, 128, 2, 2, true>(e, q, T, wk, st, maxgrid); continue; }
-        if (gen == 6 && classes[ci].C == 16 && T == 128 && wk.nq >= 2) { launch_parser2<16, 128, 2, true, true>(e, q, T, wk, st, maxgrid); continue; }
+        if (gen == 6 && classes[ci].C == 16 && T == 128 && wk.nq >= 2) { launch_parser2<16, 128, 2, 1, true>(e, q, T, wk, st, maxgrid); continue; }
         if (gen == 5 || gen == 6) {
-            if (classes[ci].C == 8 && T <= 224 && wk.nq >= 2) { launch_parser2<8, 224, 2, false>(e, q, T, wk, st, maxgrid); continue; }
+            if (classes[ci].C == 8 && T <= 224 && wk.nq >= 2) { launch_parser2<8, 224, 2, 0>(e, q, T, wk, st, maxgrid); continue; }
             // models of at most 1,024 nodes (protein families, short markers): two packed queries per CTA, parameters in
             // registers (128 registers, no spills; c4 sample: 248 vs 193 Gcell/s, bit-identical)
-            if (gen == 6 && classes[ci].C == 4 && T <= 256 && wk.nq >= 2) { launch_parser2<4, 256, 2, false>(e, q, T, wk, st, maxgrid); continue; }
-        } else if (gen >= 2 && (classes[ci].C == 4 || classes[ci].C == 8) && (classes[ci].C == 4 ? T <= 512 : T <= 384)) {
-            const bool ps = gen == 3;   // (gen 4: register variant at 2 CTAs/SM, experiment)
-            if (classes[ci].C == 4) {
-                if (T <= 256) { if (ps) launch_parser2<4, 256, 2, true>(e, q, T, wk, st, maxgrid); else launch_parser2<4, 256, 2, false>(e, q, T, wk, st, maxgrid); }
-                else { if (ps) launch_parser2<4, 512, 1, true>(e, q, T, wk, st, maxgrid); else launch_parser2<4, 512, 1, false>(e, q, T, wk, st, maxgrid); }
-            } else {
-                if (T <= 224 && ps) launch_parser2<8, 224, 2, true>(e, q, T, wk, st, maxgrid);   // 146 registers available at 2 CTAs/SM
-                else if (T <= 224 && gen == 4) launch_parser2<8, 224, 2, false>(e, q, T, wk, st, maxgrid);   // experiment: register variant capped for 2 CTAs/SM
-                else if (T <= 256) { if (ps) launch_parser2<8, 256, 2, true>(e, q, T, wk, st, maxgrid); else launch_parser2<8, 256, 1, false>(e, q, T, wk, st, maxgrid); }
-                else { if (ps) launch_parser2<8, 384, 1, true>(e, q, T, wk, st, maxgrid); else launch_parser2<8, 384, 1, false>(e, q, T, wk, st, maxgrid); }
-            }
-            continue;
+            if (gen == 6 && classes[ci].C == 4 && T <= 256 && wk.nq >= 2) { launch_parser2<4, 256, 2, 0>(e, q, T, wk, st, maxgrid); continue; }
         }
         switch (classes[ci].C) {
             case 4: if (T <= 256) launch_parser<4, 256, 2>(e, q, T, wk, st, maxgrid); else launch_parser<4, 512, 1>(e, q, T, wk, st, maxgrid); break;
