@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round-2 GPU call 9: the profile set of the truncated bench command with outputs that fit gpurun's 64 MiB return limit
+# Round-2 profile set (GPU calls 9 and 18): the profile set of the truncated bench command with outputs that fit gpurun's 64 MiB return limit
 # (launch list, --set full captures of 2 parser and 4 wave launches, host phases).
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
@@ -12,7 +12,7 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:mh_p
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:wave_kernel --launch-count 4 -f -o gpurun_out/prof_r02_wave $T > gpurun_out/r02_ncu_wave.log 2>&1
 HOSTTIME_REPS=2 WITCH_TIMING=1 timeout 600 python tools/gpu_hosttime.py c2 4 > gpurun_out/r02_host_phases.txt 2>&1
 grep -E "pipe.run" gpurun_out/r02_host_phases.txt >> $L
-for g in 1 5 4; do WITCH_PARSER=$g timeout 300 python tools/gpu_perf_c2.py 640 48 gen$g 2>&1 | grep -E "^\[|vs base" >> $L; done
+
 ls -la gpurun_out/*.ncu-rep >> $L
 du -sm gpurun_out >> $L
 sz=$(du -sm gpurun_out | cut -f1)

@@ -42,7 +42,10 @@ class EHMM:
 
     def close(self):
         if getattr(self, "_h", None):
-            _lib.load().witch_ehmm_destroy(self._h)
+            try:
+                _lib.load().witch_ehmm_destroy(self._h)
+            except TypeError:   # interpreter shutdown: module globals are already gone
+                pass
             self._h = None
 
     __del__ = close
@@ -81,7 +84,10 @@ class Queries:
 
     def close(self):
         if getattr(self, "_h", None):
-            _lib.load().witch_queries_destroy(self._h)
+            try:
+                _lib.load().witch_queries_destroy(self._h)
+            except TypeError:   # interpreter shutdown: module globals are already gone
+                pass
             self._h = None
 
     __del__ = close
