@@ -145,6 +145,52 @@ def test_edge_cases(wb, tmp_path):
         wb.align(E, Q, [99], [0])      # pair index out of range
 
 
+@pytest.mark.parametrize("root_len,degenerate", [(600, False), (1500, False), (1500, True), (1750, False), (1750, True), (2600, False)])
+def test_parser_classes_vs_oracle(wb, tmp_path, root_len, degenerate):
+    """Every launch class of the packed two-query parser (witch_abi.cu:s_classes) against the float64 oracle: C = 4 pairs
+    (<= 1,024 nodes), 13 x 128 (<= 1,664), 16 x 128 (<= 2,048, plain ACGT only), 13 x 256 (<= 3,328), and the fall-back
+    classes when degenerate symbols leave no room for two CTAs' tables. An odd number of queries of very unequal
+    lengths: the last one is paired with itself, partners differ in length by up to 10x, one query is empty."""
+    import synth
+    wl = synth.make_workload(str(tmp_path), alphabet="dna", n_total=150, n_backbone=40, root_len=root_len, decomp=10,
+                             frag_frac=0.6, frag_mean=max(150, root_len // 6), seed=31 + root_len)
+    paths = wl["hmm_paths"][:6]
+    rng = np.random.default_rng(root_len)
+    seqs = [wl["seqs"][i] for i in rng.choice(len(wl["seqs"]), size=20, replace=False)]
+    seqs += [seqs[0][:37], seqs[1][:5], "", seqs[2][: len(seqs[2]) // 2]]
+    seqs.append(seqs[3])   # 25 queries: odd
+    if degenerate:   # 11 IUPAC codes on top of ACGT -> 15 distinct symbols: the 13 x 128 class no longer fits twice per SM
+        codes = "NRYKMSWBDHV"
+        for z in range(0, 12):
+            a = list(seqs[z])
+            for pos in rng.integers(0, len(a), 6):
+                a[pos] = codes[(z + pos) % len(codes)]
+            seqs[z] = "".join(a)
+    E = wb.EHMM(paths)
+    Q = wb.Queries(E, seqs)
+    sc, rep, pre, fl = wb.score(E, Q)
+    profs = [O.Profile(p) for p in paths]
+    worst = wpre = 0.0
+    for qi, s in enumerate(seqs):
+        for h, p in enumerate(profs):
+            if len(s) == 0:
+                assert not rep[qi, h]
+                continue
+            r = O.score_pair(p, p.abc.digitize(s))
+            assert bool(rep[qi, h]) == r["reported"], (root_len, qi, h)
+            assert (int(fl[qi, h]) & 1) == (r["flags"] & 1), (root_len, qi, h)
+            wpre = max(wpre, abs(float(pre[qi, h]) - r["pre_score"]))
+            if r["reported"]:
+                worst = max(worst, abs(float(sc[qi, h]) - r["score"]))
+    assert wpre < SCORE_TOL_BITS and worst < SCORE_TOL_BITS, (root_len, wpre, worst)
+    # the same queries in another order (other partners, other pair slots) give the same numbers
+    perm = rng.permutation(len(seqs))
+    sc2, rep2, pre2, _ = wb.score(E, wb.Queries(E, [seqs[i] for i in perm]))
+    ne = np.array([len(seqs[i]) > 0 for i in perm])   # (an empty query has no Forward score: its `pre` entry is not defined)
+    assert np.array_equal(rep2, rep[perm]) and np.allclose(sc2, sc[perm], equal_nan=True, atol=1e-5)
+    assert np.allclose(pre2[ne], pre[perm][ne], atol=1e-5)
+
+
 def test_properties_at_scale(wb, tmp_path):
     """Size-independent properties on a workload the oracle could not finish quickly."""
     import synth
