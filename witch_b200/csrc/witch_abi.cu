@@ -154,6 +154,59 @@ struct witch_ehmm {
     }
 };
 
+// Device buffers of a query set come from a small per-device pool: a stage loop that creates and destroys one query set
+// per batch then issues no cudaMalloc/cudaFree at all (cudaFree synchronises the device and was measured at up to 160 ms
+// per call next to a polling nvidia-smi). Blocks are reused when they are at most 2x the request; at most 12 blocks / 1 GB
+// are kept, the rest is freed as before.
+struct QueryPool {
+    struct Block { void *p; size_t bytes; int device; };
+    std::mutex mu;
+    std::vector<Block> free_blocks;
+    size_t kept = 0;
+    void *get(size_t bytes, int device, size_t *got) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            int best = -1;
+            for (int i = 0; i < (int)free_blocks.size(); i++) {
+                const Block &b = free_blocks[i];
+                if (b.device == device && b.bytes >= bytes && b.bytes <= 2 * bytes + 4096 && (best < 0 || b.bytes < free_blocks[best].bytes)) best = i;
+            }
+            if (best >= 0) {
+                Block b = free_blocks[best];
+                free_blocks.erase(free_blocks.begin() + best);
+                kept -= b.bytes;
+                *got = b.bytes;
+                return b.p;
+            }
+        }
+        void *p = nullptr;
+        CUDA_TRY(cudaMalloc(&p, std::max<size_t>(bytes, 256)));
+        *got = std::max<size_t>(bytes, 256);
+        return p;
+    }
+    void put(void *p, size_t bytes, int device) {
+        if (!p) return;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            if (free_blocks.size() < 12 && kept + bytes <= ((size_t)1 << 30)) { free_blocks.push_back({p, bytes, device}); kept += bytes; return; }
+        }
+        cudaFree(p);
+    }
+};
+static QueryPool g_qpool;
+template <typename T>
+struct PoolBuf {
+    T *p = nullptr;
+    size_t bytes = 0;
+    int device = 0;
+    void upload(const std::vector<T> &v, int dev) {
+        device = dev;
+        p = (T *)g_qpool.get(v.size() * sizeof(T), dev, &bytes);
+        if (!v.empty()) CUDA_TRY(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, nullptr));
+    }
+    ~PoolBuf() { g_qpool.put(p, bytes, device); }
+};
+
 struct witch_queries {
     int device = 0, n = 0, nsym = 0, alph = 0;
     std::vector<int> len;
@@ -161,9 +214,9 @@ struct witch_queries {
     int symrow[MAX_SYM];
     int maxlen = 0;
     long long total = 0;
-    DevBuf<uint8_t> dsq;
-    DevBuf<long long> doff;
-    DevBuf<int> dlen;
+    PoolBuf<uint8_t> dsq;
+    PoolBuf<long long> doff;
+    PoolBuf<int> dlen;
     DevQueries view() const {
         DevQueries v;
         v.dsq = dsq.p; v.off = doff.p; v.len = dlen.p; v.n = n; v.nsym = nsym;
@@ -359,7 +412,7 @@ extern "C" int witch_queries_create(const witch_ehmm *e, int n, const char *resi
         }
         for (int i = q->nsym; i < MAX_SYM; i++) q->symrow[i] = 0;
         require_device();
-        q->dsq.upload(codes); q->doff.upload(q->off); q->dlen.upload(q->len);
+        q->dsq.upload(codes, q->device); q->doff.upload(q->off, q->device); q->dlen.upload(q->len, q->device);
         CUDA_TRY(cudaDeviceSynchronize());
         *out = q;
         return WITCH_OK;
