@@ -3,10 +3,14 @@
 // both). Same mapping (thread j owns C consecutive columns, one barrier per Forward row, two per Backward row, the D->D
 // chain as an affine scan), same arithmetic per query -- the transition parameters and every scan coefficient belong to
 // the HMM and are shared by the pair, so they stay single registers (packed instructions take a scalar broadcast
-// operand) or, with PSMEM, live in shared memory next to the emission rows. What changes is the issue-slot count per DP
-// cell (~0.55x) and that every thread carries two independent dependency chains.
+// operand) or live in shared memory next to the emission rows (PMODE: 0 = all nine parameter sets in registers, 1 = all in
+// shared memory, 2 = the six on the row's dependency chain in registers, MI / II / entry in shared memory).
+// The shape that pays on a B200: 128-thread CTAs, 13 columns per thread (C % 4 != 0: shared-memory rows are
+// [C/4][T][4] + a [T][C%4] tail), PMODE 2, compile-time CTA size (FIXT: every shared-memory offset is an immediate) --
+// 245 registers, no spills, 2 CTAs/SM, half the warp instructions per cell of the one-query kernel.
 // The queries of a pair are aligned by row index; A is the longer one. B's Forward runs on past its own end (its total is
-// captured at row L_B), B's Backward starts when row L_B is reached (its state is exactly zero before).
+// captured at row L_B), B's Backward starts when row L_B is reached (its state is exactly zero before). A lone last query
+// is paired with itself (second result dropped).
 #pragma once
 #include "parser_kernel.cuh"
 
