@@ -105,7 +105,14 @@ static void run_wave_host_items(witch_ehmm *e, witch_queries *q, const std::vect
     if (in.empty()) return;
     const int GW = 4;   // warps per CTA of every wave kernel instantiation used above
     std::vector<std::vector<WaveItem>> buckets(WL_BUCKETS);
-    for (auto &it : in) buckets[wl_bucket(it.Ls, e->M[it.h])].push_back(it);
+    // align stage: a launch lasts as long as its longest item (one warp walks a whole (query, HMM) pair: ~65 ms for
+    // 1,500 x 1,600 cells) and a step has about one wave of pairs, so the length classes up to 2,048 residues share ONE
+    // launch (scratch is per resident warp, sized by the longest item either way): short pairs fill in next to the long ones
+    auto bucket_of = [&](const WaveItem &it) {
+        const int b = wl_bucket(it.Ls, e->M[it.h]);
+        return (ALIGN && it.Ls <= 2048) ? 2 * 3 + (b & 1) : b;
+    };
+    for (auto &it : in) buckets[bucket_of(it)].push_back(it);
     std::vector<WaveItem> items;
     std::vector<int> gfirst, grange(2 * 16, 0);
     std::vector<WaveLaunch> launches;
