@@ -11,8 +11,18 @@ namespace witch {
 
 constexpr int WL_BUCKETS = 12;           // 6 length classes x 2 model-size classes
 constexpr int WL_SENTINEL_BUCKET = 15;   // unused slots sort behind every real bucket
+// Length classes of the envelope work lists. WITCH_WL_FINE=0 merges everything up to 2,048 residues into one launch per
+// list: measured on full c2 (round 2) the envelope kernels get 3.4 % faster (3,400 -> 3,286 ms per step: no small, badly
+// filled launches), but the STEP gets 7 % slower (6.62 -> 7.08 s): one long persistent launch holds every SM's register
+// file until it drains, so the multi-domain branch on the side stream (md_trace_kernel, ~1.1 s of dependent steps) can no
+// longer slip in at a launch boundary and run next to the envelope pass. The finer classes stay the default; the align
+// stage, which has no side stream next to it, merges its classes in run_wave_host_items.
+#ifndef WITCH_WL_FINE
+#define WITCH_WL_FINE 1
+#endif
 __host__ __device__ inline int wl_length_class(int Ls) {
-    return Ls <= 256 ? 0 : Ls <= 512 ? 1 : Ls <= 1024 ? 2 : Ls <= 2048 ? 3 : Ls <= 4096 ? 4 : 5;
+    if (WITCH_WL_FINE) return Ls <= 256 ? 0 : Ls <= 512 ? 1 : Ls <= 1024 ? 2 : Ls <= 2048 ? 3 : Ls <= 4096 ? 4 : 5;
+    return Ls <= 2048 ? 3 : Ls <= 4096 ? 4 : 5;
 }
 __host__ __device__ inline int wl_bucket(int Ls, int M) { return 2 * wl_length_class(Ls) + (M > 13 * 256 ? 1 : 0); }
 __host__ __device__ inline unsigned long long wl_key(int bucket, int hrank, int Ls) {
