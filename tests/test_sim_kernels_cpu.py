@@ -41,6 +41,17 @@ def test_simulated_kernels_match_oracle_amino_lane_exponents(simlib):
     _run([simlib, "amino_small", "3", "2"])          # per-lane scaling exponents (LANE_EXP) and the C = 4 parser class
 
 
+def test_simulated_packed_parser_classes(simlib):
+    """The launch classes of the two-queries-per-CTA parser (parser2_kernel.cuh, witch_abi.cu:s_classes) as written: 13 columns x
+    128 threads with the hybrid register / shared-memory parameter sets (M = 1,052; an odd number of queries, so the last one
+    is paired with itself), 13 x 256 (M = 2,6xx), and the generation-5 / generation-1 fall-back classes on the same inputs."""
+    out = _run([simlib, "dna_sub8", "3", "1"])
+    assert "0 differ" in out
+    _run([simlib, "dna_full", "2", "0"])
+    _run([simlib, "dna_sub8", "3", "0"], env={"WITCH_PARSER": "5"})
+    _run([simlib, "dna_sub8", "2", "0"], env={"WITCH_PARSER": "1"})
+
+
 def test_simulated_multidomain_branch_matches_oracle(simlib):
     """md_kernel.cuh (HMMER's stochastic-trace clustering for regions that fail the single-domain test) exactly as
     written, against oracle/hmm_md.c, which is itself pinned to clusters captured from inside the reference binary:
