@@ -120,3 +120,45 @@ def test_synthetic_workload_is_seeded_and_consistent(tmp_path):
     assert prof.nseq == a["nseq"][0]
     r = O.score_pair(prof, prof.abc.digitize(a["seqs"][0]))
     assert r["reported"] and r["score"] > 10
+
+
+def test_bench_slabs_weak_and_strong():
+    """bench.py's batches: length-stratified slabs that partition the query set; weak scaling = `world` copies of a slab
+    (copies > 0 mutated, lengths unchanged), strong scaling = the slab itself."""
+    sys.path.insert(0, ROOT)
+    import bench
+    rng = np.random.default_rng(3)
+    seqs = ["".join(rng.choice(list("ACGT"), size=int(n))) for n in rng.integers(50, 400, 101)]
+    wl = {"seqs": seqs, "meta": {"alphabet": "dna"}}
+    weak = bench.make_slabs(wl, 4, 3)
+    strong = bench.make_slabs(wl, 4, 3, strong=True)
+    ids = np.sort(np.concatenate([s[2] for s in weak]))
+    assert np.array_equal(ids, np.arange(len(seqs)))                      # the slabs partition the set
+    tot = [int(np.diff(s[1]).sum()) for s in strong]
+    assert max(tot) - min(tot) < 0.15 * max(tot)                          # ... into batches of similar residue counts
+    for (rw, ow, iw), (rs, os_, is_) in zip(weak, strong):
+        assert np.array_equal(iw, is_) and len(ow) == 3 * len(is_) + 1 and len(os_) == len(is_) + 1
+        assert len(rw) == 3 * len(rs) and np.array_equal(rw[:len(rs)], rs)     # copy 0 is the slab itself
+        assert np.array_equal(np.diff(ow)[:len(is_)], np.diff(os_))
+        m = rw[len(rs):2 * len(rs)] != rs
+        assert 0 < m.mean() < 0.05                                            # copy 1: ~2 % point mutations
+        assert "".join(seqs[i] for i in is_).encode() == rs.tobytes()
+
+
+def test_bench_reference_arm_prints_one_json_line(tmp_path):
+    """`bench.py --impl reference` (the reference's HMMER binaries from oracle/_ref on the host cores): one JSON line on
+    stdout with the contract's keys; skipped when the binaries are not staged."""
+    import json
+    import subprocess
+    from oracle.make_ref import have_ref
+    if not have_ref():
+        pytest.skip("oracle/_ref (the reference's HMMER binaries) is not staged")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "tiny", "--steps", "1",
+                        "--warmup", "0", "--cpu-seconds", "1", "--workdir", str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "GCUPS" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["config"]["workload"] == "tiny"
